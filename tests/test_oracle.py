@@ -1,0 +1,241 @@
+"""CPU tests of the oracle itself: golden vectors, known answers, independent cross-checks.
+
+The oracle (oracle/stn_numpy.py, oracle/stn_oracle.c) is the checker every GPU parity test leans on, so
+it is pinned here first -- against the reference's own rotation-dropout file (golden vectors), against
+analytic answers derivable from the reference (SURVEY.md 8c KATs), and against torch's independent
+affine_grid / grid_sample.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from loans_b200 import workloads as W
+from oracle import stn_c as oc
+from oracle import stn_numpy as on
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class _SeededGlobalStream:
+    """numpy's legacy global stream, seeded like the golden generator seeded it."""
+
+    def __init__(self, seed):
+        self.state = np.random.RandomState(int(seed))
+
+    def rand(self, n):
+        return self.state.rand(n)
+
+
+# ----------------------------------------------------------------------------- a1 pinned to the reference
+def test_rotation_dropout_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "rotation_dropout.npz"))
+    n = int(g["n_cases"])
+    assert n == 40
+    seen_flags = set()
+    for i in range(n):
+        p = "c%03d_" % i
+        train, ratio, seed = g[p + "meta"]
+        train = bool(train)
+        m = on.rotation_dropout_mask_value(ratio, train, _SeededGlobalStream(seed))
+        seen_flags.add((train, float(m)))
+        for impl in (on, oc):
+            y = impl.rotation_dropout_forward(g[p + "theta"], m)
+            assert y.dtype == np.float32
+            assert np.array_equal(y, g[p + "y"]), (i, impl.__name__)
+            if train:
+                gt = impl.rotation_dropout_backward(g[p + "gy"], m)
+                assert np.array_equal(gt, g[p + "gtheta"]), (i, impl.__name__)
+    # both Bernoulli outcomes and the test-mode scaling were exercised
+    assert (True, 0.0) in seen_flags and (True, 1.0) in seen_flags and (False, 0.25) in seen_flags
+
+
+def test_rotation_dropout_ratio_zero_is_separable_in_both_modes():
+    # LoANs always calls rotation_dropout(..., ratio=0.0) (sheep/sheep_localizer.py:61,169)
+    theta = W.make_theta(np.random.default_rng(0), 5, rotate=True)
+    for train in (True, False):
+        m = on.rotation_dropout_mask_value(0.0, train, _SeededGlobalStream(7))
+        y = on.rotation_dropout_forward(theta, m)
+        assert np.all(y[:, 0, 1] == 0) and np.all(y[:, 1, 0] == 0)
+        assert np.array_equal(y[:, [0, 1], [0, 1]], theta[:, [0, 1], [0, 1]])
+        assert np.array_equal(y[:, :, 2], theta[:, :, 2])
+
+
+def test_rotation_dropout_type_check():
+    with pytest.raises(AssertionError):
+        on.rotation_dropout_forward(np.zeros((2, 3, 2), np.float32), 1.0)
+
+
+# ----------------------------------------------------------------------------- known answers
+def _identity(b):
+    return np.tile(np.array([[1, 0, 0], [0, 1, 0]], np.float32), (b, 1, 1))
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_identity_theta_reproduces_frame(impl):
+    x = np.random.default_rng(1).random((2, 3, 11, 17), dtype=np.float32)
+    y, grid = impl.crop_forward(x, _identity(2), (11, 17))
+    assert np.array_equal(y, x)
+    assert grid[0, 0, 0, 0] == -1 and grid[0, 0, 0, -1] == 1 and grid[0, 1, 0, 0] == -1 and grid[0, 1, -1, 0] == 1
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_constant_frame_and_affine_ramp(impl):
+    h, w = 24, 31
+    theta = np.array([[[0.6, 0.1, 0.05], [-0.08, 0.7, -0.1]]], np.float32)
+    const = np.full((1, 1, h, w), 0.375, np.float32)
+    y, grid = impl.crop_forward(const, theta, (9, 13))
+    assert np.allclose(y, 0.375, rtol=0, atol=1e-7)
+    jj, ii = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    ramp = (0.01 * jj + 0.02 * ii + 0.1).astype(np.float32)[None, None]
+    y, grid = impl.crop_forward(ramp, theta, (9, 13))
+    u = (grid[0, 0].astype(np.float64) + 1) * (w - 1) / 2
+    v = (grid[0, 1].astype(np.float64) + 1) * (h - 1) / 2
+    assert np.allclose(y[0, 0], 0.01 * u + 0.02 * v + 0.1, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_box_outside_frame_is_zero_and_cuts_gradients(impl):
+    x = np.random.default_rng(2).random((1, 3, 12, 12), dtype=np.float32) + 1.0
+    theta = np.array([[[0.3, 0, 3.0], [0, 0.3, 0.0]]], np.float32)       # > 1 px right of the frame
+    y, _ = impl.crop_forward(x, theta, (6, 6))
+    assert np.all(y == 0)
+    gy = np.ones_like(y)
+    gtheta, gx, ggrid = impl.crop_backward(x, theta, (6, 6), gy)
+    assert np.all(gx == 0) and np.all(ggrid[:, 0] == 0) and np.all(gtheta[:, 0] == 0)
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_loans_initial_theta_and_bbox_convention(impl):
+    # sheep/sheep_localizer.py:30-33 bias [0.8,0,0,0,0.8,0]; :84-91 corner convention
+    theta = np.tile(np.array([[0.8, 0, 0], [0, 0.8, 0]], np.float32), (3, 1, 1))
+    grid = impl.grid_forward(theta, (75, 75))
+    top, left = grid[:, 1, 0, 0], grid[:, 0, 0, 0]
+    bottom, right = grid[:, 1, -1, -1], grid[:, 0, -1, -1]
+    f = np.float32(0.8)
+    assert np.all(top == -f) and np.all(left == -f) and np.all(bottom == f) and np.all(right == f)
+
+
+def test_border_band_reads_zero_padding():
+    # a sample between the last pixel and one pixel outside interpolates towards 0
+    x = np.ones((1, 1, 4, 4), np.float32)
+    grid = np.zeros((1, 2, 1, 1), np.float32)
+    grid[0, 0] = 1.0 + (2.0 / 3.0) * 0.25            # u = 3.25 in unpadded pixels
+    y = on.sampler_forward(x, grid)
+    assert np.allclose(y, 0.75, atol=1e-6)
+    assert np.array_equal(y, oc.sampler_forward(x, grid))
+
+
+# ----------------------------------------------------------------------------- C restatement == numpy restatement
+CASES = [
+    # b, k, c, h, w, oh, ow, mask
+    (3, 1, 3, 19, 23, 8, 11, 1.0),
+    (2, 1, 1, 7, 5, 16, 12, 1.0),        # up-sampling, C=1
+    (4, 1, 3, 32, 32, 10, 10, 0.0),      # separable (LoANs' case)
+    (2, 4, 3, 20, 28, 6, 9, 0.0),        # K crops per frame
+    (2, 3, 2, 15, 15, 5, 4, 0.5),        # test-mode scaling of the rotation terms, K=3
+    (1, 1, 3, 6, 6, 1, 7, 1.0),          # oH == 1
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_c_oracle_is_bitwise_the_numpy_oracle(case):
+    b, k, c, h, w, oh, ow, mask = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = rng.random((b, c, h, w), dtype=np.float32)
+    theta = W.make_theta(rng, b * k, rotate=True)
+    theta[::3, :, 2] += 0.7                                   # some boxes partly outside
+    gy = rng.standard_normal((b * k, c, oh, ow), dtype=np.float32)
+    gg = rng.standard_normal((b * k, 2, oh, ow), dtype=np.float32)
+    y1, g1 = on.crop_forward(x, theta, (oh, ow), mask, k)
+    y2, g2 = oc.crop_forward(x, theta, (oh, ow), mask, k)
+    assert np.array_equal(g1, g2) and np.array_equal(y1, y2)
+    t1, gx1, gg1 = on.crop_backward(x, theta, (oh, ow), gy, gg, mask, k)
+    t2, gx2, gg2 = oc.crop_backward(x, theta, (oh, ow), gy, gg, mask, k)
+    assert np.array_equal(gg1, gg2) and np.array_equal(gx1, gx2)
+    # gtheta goes through an sgemm over oH*oW terms in numpy and a float64 sum in C
+    assert np.allclose(t1, t2, rtol=0, atol=2e-6 * max(1.0, np.abs(t2).max()))
+
+
+def test_c_oracle_unfused_entry_points():
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 9, 14), dtype=np.float32)
+    grid = rng.uniform(-1.3, 1.3, (2, 2, 5, 6)).astype(np.float32)      # arbitrary, not affine
+    gy = rng.standard_normal((2, 3, 5, 6), dtype=np.float32)
+    assert np.array_equal(on.sampler_forward(x, grid), oc.sampler_forward(x, grid))
+    gx1, gg1 = on.sampler_backward(x, grid, gy)
+    gx2, gg2 = oc.sampler_backward(x, grid, gy)
+    assert np.array_equal(gx1, gx2) and np.array_equal(gg1, gg2)
+    assert np.allclose(on.grid_backward(gg1), oc.grid_backward(gg1), rtol=0, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- independent implementation (torch)
+@pytest.mark.parametrize("smooth", [True, False])
+def test_against_torch_affine_grid_and_grid_sample(smooth):
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    b, c, h, w, oh, ow = 4, 3, 40, 56, 17, 13
+    x = W.make_frames(rng, b, c, h, w, smooth=smooth)
+    theta = W.make_theta(rng, b, rotate=True)
+    theta[0, 0, 2] = 0.55
+    gy = rng.standard_normal((b, c, oh, ow), dtype=np.float32)
+    y, grid = on.crop_forward(x, theta, (oh, ow))
+    gtheta, gx, _ = on.crop_backward(x, theta, (oh, ow), gy)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    tt = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    g = F.affine_grid(tt, (b, c, oh, ow), align_corners=True)
+    yt = F.grid_sample(xt, g, mode="bilinear", padding_mode="zeros", align_corners=True)
+    yt.backward(torch.tensor(gy, dtype=torch.float64))
+    rel = lambda a, r: np.abs(a - r).max() / np.abs(r).max()            # noqa: E731
+    assert rel(grid, g.detach().numpy().transpose(0, 3, 1, 2)) < 2e-7
+    assert rel(y, yt.detach().numpy()) < (5e-6 if smooth else 1e-5)
+    assert rel(gx, xt.grad.numpy()) < 1e-5
+    assert rel(gtheta, tt.grad.numpy()) < (1e-5 if smooth else 1e-4)
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_gradients_on_affine_ramp_are_analytic(impl):
+    # x = a*col + b*row + c  =>  y = a*u + b*v + c  =>  dy/du = a, dy/dv = b wherever the box is inside
+    h, w, oh, ow = 30, 40, 7, 9
+    a, b_, c0 = 0.015625, -0.03125, 2.0                       # exactly representable slopes
+    jj, ii = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    x = (a * jj + b_ * ii + c0).astype(np.float32)[None, None]
+    theta = np.array([[[0.6, 0.15, 0.1], [-0.1, 0.5, -0.05]]], np.float32)
+    gy = np.random.default_rng(4).standard_normal((1, 1, oh, ow), dtype=np.float32)
+    gtheta, gx, ggrid = impl.crop_backward(x, theta, (oh, ow), gy)
+    assert np.allclose(ggrid[0, 0], gy[0, 0] * a * (w - 1) / 2, rtol=0, atol=2e-5)
+    assert np.allclose(ggrid[0, 1], gy[0, 0] * b_ * (h - 1) / 2, rtol=0, atol=2e-5)
+    want = impl.grid_backward(np.stack([gy[0] * a * (w - 1) / 2, gy[0] * b_ * (h - 1) / 2], axis=1))
+    assert np.allclose(gtheta, want, rtol=0, atol=2e-4)
+    # bilinear weights sum to one: every gy lands somewhere in gx exactly once
+    assert abs(float(gx.astype(np.float64).sum()) - float(gy.astype(np.float64).sum())) < 1e-4
+
+
+# ----------------------------------------------------------------------------- committed fixtures
+def test_stn_small_golden_replay():
+    g = np.load(os.path.join(GOLDEN, "stn_small.npz"))
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        osz = tuple(int(v) for v in g[p + "out_size"])
+        mask = float(g[p + "mask"])
+        for impl in (on, oc):
+            y, grid = impl.crop_forward(g[p + "x"], g[p + "theta"], osz, mask)
+            assert np.array_equal(grid, g[p + "grid"]) and np.array_equal(y, g[p + "y"])
+            gt, gx, gg = impl.crop_backward(g[p + "x"], g[p + "theta"], osz, g[p + "gy"], g[p + "ggrid_up"], mask)
+            assert np.array_equal(gx, g[p + "gx"]) and np.array_equal(gg, g[p + "ggrid"])
+            assert np.allclose(gt, g[p + "gtheta"], rtol=0, atol=2e-6 * max(1.0, np.abs(g[p + "gtheta"]).max()))
+
+
+def test_shard_invariance():
+    # the path shards by batch with no exchange: concat of shards == full batch
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=6, rotate=True)
+    osz = (wl.out_h, wl.out_w)
+    y, grid = oc.crop_forward(d["x"], d["theta"], osz)
+    gt, gx, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"])
+    for lo, hi in ((0, 3), (3, 6)):
+        ys, gs = oc.crop_forward(d["x"][lo:hi], d["theta"][lo:hi], osz)
+        gts, gxs, _ = oc.crop_backward(d["x"][lo:hi], d["theta"][lo:hi], osz, d["gy"][lo:hi])
+        assert np.array_equal(ys, y[lo:hi]) and np.array_equal(gs, grid[lo:hi])
+        assert np.array_equal(gts, gt[lo:hi]) and np.array_equal(gxs, gx[lo:hi])
