@@ -1,0 +1,91 @@
+/*
+ * loans_stn.h -- C ABI of the B200-native STN crop stage of LoANs (libloans_stn.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference (Bartzi/loans): the three operator calls at
+ * the end of the localizer forward,
+ *
+ *     transform_params = rotation_dropout(F.reshape(transform_params, (-1, 2, 3)), ratio=0.0)
+ *     points = F.spatial_transformer_grid(transform_params, self.out_size)
+ *     rois   = F.spatial_transformer_sampler(images, points)
+ *                                    (reference sheep/sheep_localizer.py:61-63 and :169-171)
+ *
+ * and their backward passes.  The reference is pure Python on Chainer 4.1; it has no FFI of its own, so
+ * every entry point below names the reference operator (file:line) it stands in for.  The reference-side
+ * binding (Chainer FunctionNodes over ctypes + cupy pointers) is shown in INTEGRATION.md and shipped in
+ * loans_b200/chainer_compat.py.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and ints only; every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     function name ends in _host; tensors are C-contiguous, frames NCHW;
+ *   - the library never allocates, frees or retains caller memory; outputs are fully overwritten
+ *     (gx includes its zeros); work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream) and the call returns without synchronising;
+ *   - return value 0 = success; non-zero = error, message via loans_stn_last_error() (thread-local).
+ *     Shape/dtype violations are reported before anything is launched;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ *
+ * Shapes: n = number of crops = b * k, b = frames, k = crops per frame (crop i samples frame i / k;
+ * Chainer's sampler only has k == 1), c channels, frame h x w, crop oh x ow.
+ *   theta (n,2,3) f32 | grid (n,2,oh,ow) f32, channel 0 = x, 1 = y in [-1,1], (-1,-1) = centre of the top-left
+ *   pixel | x (b,c,h,w) f32 | y, gy (n,c,oh,ow) f32 or bf16 | gx (b,c,h,w) f32 | gtheta (n,2,3) f32.
+ */
+#ifndef LOANS_STN_H_
+#define LOANS_STN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOANS_STN_ABI_VERSION 1
+
+/* element type of the crops y / gy */
+#define LOANS_STN_F32  0
+#define LOANS_STN_BF16 1     /* bf16 = round-to-nearest-even of the fp32 result; no reference equivalent
+                                (Chainer's sampler type-checks float32), defined by BASELINE.json config 3 */
+
+int loans_stn_abi_version(void);
+const char *loans_stn_last_error(void);
+/* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
+unsigned long long loans_stn_launch_count(void);
+
+/* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.
+ *      Replaces RotationDropout.forward / .backward, reference functions/rotation_droput.py:26-45 / :47-48.
+ *      mask01 is drawn ON THE HOST by the caller (train: float(rand(1) < ratio), one draw per call, :41;
+ *      test: ratio, :33-35) so the RNG stream stays the host framework's.  In-place (out == in) allowed. */
+int loans_stn_rotation_dropout(const float *theta_in, float mask01, float *theta_out, int n, void *stream);
+
+/* ---- a2  F.spatial_transformer_grid forward / backward (call site sheep/sheep_localizer.py:62,170;
+ *      arithmetic in chainer 4.1.0 chainer/functions/array/spatial_transformer_grid.py, restated in
+ *      oracle/stn_numpy.py:grid_forward/grid_backward). */
+int loans_stn_grid_fwd(const float *theta, float *grid, int n, int oh, int ow, void *stream);
+int loans_stn_grid_bwd(const float *ggrid, float *gtheta, int n, int oh, int ow, void *stream);
+
+/* ---- a3/a4  F.spatial_transformer_sampler forward / backward on an EXPLICIT (arbitrary) grid
+ *      (call site sheep/sheep_localizer.py:63,171; chainer 4.1.0 .../spatial_transformer_sampler.py,
+ *      restated in oracle/stn_numpy.py:sampler_forward/sampler_backward).
+ *      bwd: gx and/or ggrid may be NULL (skipped).  gx is zero-filled and scatter-added with
+ *      warp-aggregated float atomics (order-dependent in the last bits). */
+int loans_stn_sampler_fwd(const float *x, const float *grid, void *y,
+                          int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream);
+int loans_stn_sampler_bwd(const float *x, const float *grid, const void *gy, float *gx, float *ggrid,
+                          int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
+
+/* ---- a5  the fused composite: rotation_dropout -> grid -> sampler in ONE kernel per direction
+ *      (reference sheep/sheep_localizer.py:61-63 as a whole).
+ *      fwd: y always; grid may be NULL (not materialised).
+ *      bwd: gtheta always (already multiplied by the rotation mask, i.e. the gradient w.r.t. the
+ *           un-masked theta the localizer predicted); ggrid_upstream (n,2,oh,ow) or NULL is the gradient
+ *           arriving on the grid output from other consumers (the corner regularisers, reference
+ *           common/utils.py:142-178,301-316) and is folded into gtheta; gx may be NULL (LoANs never needs
+ *           it: frames do not require grad); ggrid_out may be NULL.
+ *           gx is produced by a deterministic gather (each element written once, no atomics). */
+int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y, float *grid,
+                       int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream);
+int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const void *gy,
+                       const float *ggrid_upstream, float *gtheta, float *gx, float *ggrid_out,
+                       int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOANS_STN_H_ */

@@ -1,0 +1,65 @@
+"""ctypes loader of libloans_stn.so (the C ABI in include/loans_stn.h).
+
+The library is built in-tree by ``loans_b200.build.build()`` (``__graft_entry__.build()`` calls it).  There is
+deliberately no fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libloans_stn.so")
+ABI_VERSION = 1
+F32, BF16 = 0, 1
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_fl = ctypes.c_float
+
+# name -> argtypes, exactly include/loans_stn.h
+SIGNATURES = {
+    "loans_stn_abi_version": [],
+    "loans_stn_last_error": [],
+    "loans_stn_launch_count": [],
+    "loans_stn_rotation_dropout": [_vp, _fl, _vp, _i, _vp],
+    "loans_stn_grid_fwd": [_vp, _vp, _i, _i, _i, _vp],
+    "loans_stn_grid_bwd": [_vp, _vp, _i, _i, _i, _vp],
+    "loans_stn_sampler_fwd": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_sampler_bwd": [_vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_crop_fwd": [_vp, _vp, _fl, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_crop_bwd": [_vp, _vp, _fl, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
+}
+
+
+class StnLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StnLibraryError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). loans_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)           # AttributeError if the ABI lost a symbol
+            fn.argtypes = argtypes
+            fn.restype = _i
+        handle.loans_stn_last_error.restype = ctypes.c_char_p
+        handle.loans_stn_launch_count.restype = ctypes.c_ulonglong
+        if handle.loans_stn_abi_version() != ABI_VERSION:
+            raise StnLibraryError("libloans_stn.so ABI %d != expected %d" % (handle.loans_stn_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise StnLibraryError("%s failed: %s" % (what, lib().loans_stn_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().loans_stn_launch_count())

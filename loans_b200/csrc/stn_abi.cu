@@ -1,0 +1,191 @@
+// stn_abi.cu -- extern "C" entry points declared in include/loans_stn.h: argument validation, error
+// reporting, launch accounting.  No torch types, no allocation, no synchronisation.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/loans_stn.h"
+#include "stn_common.cuh"
+
+namespace stn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_rotation_dropout(const float *in, float mask01, float *out, int n, cudaStream_t stream);
+int launch_grid_fwd(const float *theta, float *grid, int n, int oh, int ow, cudaStream_t stream);
+int launch_grid_bwd(const float *ggrid, float *gtheta, int n, int oh, int ow, cudaStream_t stream);
+int launch_sampler_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
+int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stream);
+int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
+
+static int need_device(const char *what)
+{
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error("%s: no usable CUDA device (%s); this library has no CPU fallback", what, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+static int check_dims(const char *what, int n, int k, int c, int h, int w, int oh, int ow)
+{
+    if (n < 0 || k < 1 || c < 1 || h < 1 || w < 1 || oh < 1 || ow < 1)
+        return set_error("%s: bad dimensions n=%d k=%d c=%d h=%d w=%d oh=%d ow=%d", what, n, k, c, h, w, oh, ow);
+    if (n % k != 0) return set_error("%s: n=%d crops is not a multiple of k=%d crops per frame", what, n, k);
+    if ((long long)h * w > 0x3fffffffLL || (long long)oh * ow > 0x3fffffffLL)
+        return set_error("%s: a single plane exceeds 2^30 elements", what);
+    return 0;
+}
+
+static int check_dtype(const char *what, int dt)
+{
+    if (dt != LOANS_STN_F32 && dt != LOANS_STN_BF16) return set_error("%s: unknown crop dtype %d", what, dt);
+    return 0;
+}
+
+static CropParams base_params(int n, int k, int c, int h, int w, int oh, int ow)
+{
+    CropParams p = {};
+    p.N = n; p.K = k; p.C = c; p.H = h; p.W = w; p.oH = oh; p.oW = ow;
+    p.mask01 = 1.0f;
+    p.xstep = ow > 1 ? 2.0 / (double)(ow - 1) : 0.0;
+    p.ystep = oh > 1 ? 2.0 / (double)(oh - 1) : 0.0;
+    return p;
+}
+
+}  // namespace stn
+
+using namespace stn;
+
+#define REQUIRE_PTR(what, ptr)                                                    \
+    do {                                                                          \
+        if ((ptr) == nullptr) return set_error("%s: %s is NULL", what, #ptr);     \
+    } while (0)
+
+extern "C" {
+
+int loans_stn_abi_version(void) { return LOANS_STN_ABI_VERSION; }
+
+const char *loans_stn_last_error(void) { return g_err; }
+
+unsigned long long loans_stn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int loans_stn_rotation_dropout(const float *theta_in, float mask01, float *theta_out, int n, void *stream)
+{
+    const char *what = "loans_stn_rotation_dropout";
+    if (n < 0) return set_error("%s: n=%d", what, n);
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, theta_in);
+    REQUIRE_PTR(what, theta_out);
+    if (need_device(what)) return 1;
+    return launch_rotation_dropout(theta_in, mask01, theta_out, n, (cudaStream_t)stream);
+}
+
+int loans_stn_grid_fwd(const float *theta, float *grid, int n, int oh, int ow, void *stream)
+{
+    const char *what = "loans_stn_grid_fwd";
+    if (check_dims(what, n, 1, 1, 1, 1, oh, ow)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, grid);
+    if (need_device(what)) return 1;
+    return launch_grid_fwd(theta, grid, n, oh, ow, (cudaStream_t)stream);
+}
+
+int loans_stn_grid_bwd(const float *ggrid, float *gtheta, int n, int oh, int ow, void *stream)
+{
+    const char *what = "loans_stn_grid_bwd";
+    if (check_dims(what, n, 1, 1, 1, 1, oh, ow)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, ggrid);
+    REQUIRE_PTR(what, gtheta);
+    if (need_device(what)) return 1;
+    return launch_grid_bwd(ggrid, gtheta, n, oh, ow, (cudaStream_t)stream);
+}
+
+int loans_stn_sampler_fwd(const float *x, const float *grid, void *y,
+                          int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream)
+{
+    const char *what = "loans_stn_sampler_fwd";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, y_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, grid);
+    REQUIRE_PTR(what, y);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.grid_in = grid; p.y = y;
+    return launch_crop_fwd(p, true, y_dtype, (cudaStream_t)stream);
+}
+
+int loans_stn_sampler_bwd(const float *x, const float *grid, const void *gy, float *gx, float *ggrid,
+                          int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream)
+{
+    const char *what = "loans_stn_sampler_bwd";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, gy_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, grid);
+    REQUIRE_PTR(what, gy);
+    if (gx == nullptr && ggrid == nullptr) return 0;
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.grid_in = grid; p.gy = gy; p.gx = gx; p.ggrid_out = ggrid;
+    return launch_sampler_bwd(p, gy_dtype, (cudaStream_t)stream);
+}
+
+int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y, float *grid,
+                       int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_fwd";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, y_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, y);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.y = y; p.grid_out = grid;
+    return launch_crop_fwd(p, false, y_dtype, (cudaStream_t)stream);
+}
+
+int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const void *gy,
+                       const float *ggrid_upstream, float *gtheta, float *gx, float *ggrid_out,
+                       int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_bwd";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, gy_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, gy);
+    REQUIRE_PTR(what, gtheta);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.ggrid_up = ggrid_upstream;
+    p.gtheta = gtheta; p.gx = gx; p.ggrid_out = ggrid_out;
+    return launch_crop_bwd(p, gy_dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

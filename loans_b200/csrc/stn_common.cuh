@@ -1,0 +1,67 @@
+// stn_common.cuh -- launch parameter block, dtype helpers and error plumbing shared by the .cu files.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "stn_math.cuh"
+
+namespace stn {
+
+constexpr int kThreads = 256;       // threads per CTA, every kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kNumSMs = 148;        // B200
+
+// One parameter block for the whole family; unused pointers are null.
+struct CropParams {
+    const float *x;          // (B,C,H,W)
+    const float *theta;      // (N,2,3)        fused path
+    const float *grid_in;    // (N,2,oH,oW)    explicit-grid path
+    float mask01;
+    void *y;                 // (N,C,oH,oW) f32|bf16
+    float *grid_out;         // (N,2,oH,oW) or null
+    const void *gy;          // (N,C,oH,oW) f32|bf16
+    const float *ggrid_up;   // (N,2,oH,oW) or null
+    float *gtheta;           // (N,2,3)
+    float *gx;               // (B,C,H,W) or null
+    float *ggrid_out;        // (N,2,oH,oW) or null
+    int N, K, C, H, W, oH, oW;
+    double xstep, ystep;     // 2/(oW-1), 2/(oH-1)
+    int px_per_cta;          // crop pixels handled by one CTA of the per-crop roles
+    int ctas_per_crop;       // == cluster size in the backward theta role
+    int theta_ctas;          // backward: CTAs [0, theta_ctas) reduce gtheta, the rest gather gx
+    int gx_tile_px;          // backward gx role: frame pixels per tile
+    int gx_tiles_per_frame;
+};
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ float load(const float *p, size_t i) { return __ldg(p + i); }
+    static __device__ __forceinline__ void store(float *p, size_t i, float v) { p[i] = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float load(const __nv_bfloat16 *p, size_t i)
+    {
+        return __bfloat162float(__ldg(p + i));
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, size_t i, float v)
+    {
+        p[i] = __float2bfloat16_rn(v);
+    }
+};
+
+// xs[0..oW) and ys[0..oH) into shared memory (numpy.linspace(-1,1,n,dtype=float32), see stn_math.cuh)
+__device__ __forceinline__ void fill_axis_tables(float *xs, float *ys, int oW, int oH, double xstep, double ystep)
+{
+    for (int k = threadIdx.x; k < oW + oH; k += blockDim.x) {
+        if (k < oW) xs[k] = linspace_pm1(k, oW, xstep);
+        else ys[k - oW] = linspace_pm1(k - oW, oH, ystep);
+    }
+}
+
+// ---- host-side error plumbing (definitions in stn_abi.cu)
+int set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char *what);
+
+}  // namespace stn

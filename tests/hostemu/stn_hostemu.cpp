@@ -1,0 +1,107 @@
+// Host emulation harness -- TEST INFRASTRUCTURE ONLY, never loaded by the product.
+// Runs the per-pixel device code of loans_b200/csrc/stn_math.cuh (the same header the CUDA kernels include)
+// on the CPU, pixel by pixel, so that the arithmetic and above all the inverse-mapping gather for gx can be
+// checked against the oracle in the CPU-only container.  Built with g++ -ffp-contract=off by
+// tests/test_hostemu.py.
+#include <cstddef>
+#include <vector>
+
+#include "../../loans_b200/csrc/stn_math.cuh"
+
+using namespace stn;
+
+struct LoadF {
+    float operator()(const float *p, size_t i) const { return p[i]; }
+};
+
+extern "C" {
+
+void emu_crop_fwd(const float *x, const float *theta, float mask01, float *y, float *grid,
+                  int n, int k, int c, int h, int w, int oh, int ow)
+{
+    const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
+    const int npx = oh * ow;
+    const size_t plane = (size_t)h * w;
+    for (int b = 0; b < n; ++b) {
+        const Theta th = load_theta_masked(theta + 6 * b, mask01);
+        const float *xb = x + (size_t)(b / k) * c * plane;
+        for (int q = 0; q < npx; ++q) {
+            const int i = q / ow, j = q - i * ow;
+            const float xs = linspace_pm1(j, ow, xstep), ys = linspace_pm1(i, oh, ystep);
+            const float g0 = grid_elem(th.t00, th.t01, th.t02, xs, ys), g1 = grid_elem(th.t10, th.t11, th.t12, xs, ys);
+            if (grid) { grid[(size_t)b * 2 * npx + q] = g0; grid[(size_t)b * 2 * npx + npx + q] = g1; }
+            const Tap t = make_tap(g0, g1, h, w);
+            const TapAddr a = make_tap_addr(t, h, w);
+            const Weights4 wt = make_weights(t);
+            for (int ch = 0; ch < c; ++ch) {
+                float x1, x2, x3, x4;
+                load_taps(xb + ch * plane, a, w, x1, x2, x3, x4);
+                y[((size_t)b * c + ch) * npx + q] = interp(wt, x1, x2, x3, x4);
+            }
+        }
+    }
+}
+
+void emu_crop_bwd(const float *x, const float *theta, float mask01, const float *gy, const float *ggrid_up,
+                  float *gtheta, float *gx, float *ggrid_out, int n, int k, int c, int h, int w, int oh, int ow)
+{
+    const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
+    const int npx = oh * ow;
+    const size_t plane = (size_t)h * w;
+    std::vector<float> xs(ow), ys(oh);
+    for (int j = 0; j < ow; ++j) xs[j] = linspace_pm1(j, ow, xstep);
+    for (int i = 0; i < oh; ++i) ys[i] = linspace_pm1(i, oh, ystep);
+    for (int b = 0; b < n; ++b) {
+        const Theta th = load_theta_masked(theta + 6 * b, mask01);
+        const float *xb = x + (size_t)(b / k) * c * plane;
+        const float *gyb = gy + (size_t)b * c * npx;
+        float s[6] = {0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < npx; ++q) {
+            const int i = q / ow, j = q - i * ow;
+            const Tap t = make_tap(grid_elem(th.t00, th.t01, th.t02, xs[j], ys[i]),
+                                   grid_elem(th.t10, th.t11, th.t12, xs[j], ys[i]), h, w);
+            const TapAddr a = make_tap_addr(t, h, w);
+            float su = 0, sv = 0;
+            for (int ch = 0; ch < c; ++ch) {
+                float x1, x2, x3, x4, gu, gv;
+                load_taps(xb + ch * plane, a, w, x1, x2, x3, x4);
+                grad_uv(t, x1, x2, x3, x4, gu, gv);
+                const float g = gyb[(size_t)ch * npx + q];
+                gu = f_mul(gu, g); gv = f_mul(gv, g);
+                if (ch == 0) { su = gu; sv = gv; } else { su = f_add(su, gu); sv = f_add(sv, gv); }
+            }
+            finish_grad_uv(t, h, w, su, sv);
+            if (ggrid_out) { ggrid_out[(size_t)b * 2 * npx + q] = su; ggrid_out[(size_t)b * 2 * npx + npx + q] = sv; }
+            if (ggrid_up) {
+                su = f_add(su, ggrid_up[(size_t)b * 2 * npx + q]);
+                sv = f_add(sv, ggrid_up[(size_t)b * 2 * npx + npx + q]);
+            }
+            s[0] += su * xs[j]; s[1] += su * ys[i]; s[2] += su;
+            s[3] += sv * xs[j]; s[4] += sv * ys[i]; s[5] += sv;
+        }
+        s[1] = f_mul(s[1], mask01); s[3] = f_mul(s[3], mask01);
+        for (int e = 0; e < 6; ++e) gtheta[6 * b + e] = s[e];
+    }
+    if (!gx) return;
+    const int frames = n / k;
+    std::vector<InvCrop> inv(k);
+    for (int f = 0; f < frames; ++f) {
+        for (int kk = 0; kk < k; ++kk)
+            inv[kk] = make_inv_crop(load_theta_masked(theta + 6 * (f * k + kk), mask01), h, w, oh, ow);
+        for (int r = 0; r < h; ++r)
+            for (int sx = 0; sx < w; ++sx)
+                for (int c0 = 0; c0 < c; c0 += 3) {
+                    const int nc = c - c0 < 3 ? c - c0 : 3;
+                    float acc[3] = {0, 0, 0};
+                    for (int kk = 0; kk < k; ++kk)
+                        gather_from_crop<3>(inv[kk], xs.data(), ys.data(), h, w, oh, ow, r + 1, sx + 1,
+                                            gy + ((size_t)(f * k + kk) * c + c0) * npx, nc, LoadF(), acc);
+                    for (int ch = 0; ch < nc; ++ch) gx[((size_t)f * c + c0 + ch) * plane + (size_t)r * w + sx] = acc[ch];
+                }
+    }
+}
+
+// number of (i, j) candidates the scanline enumeration visits for one frame -- efficiency probe for tests
+long long emu_count_candidates(const float *theta, float mask01, int h, int w, int oh, int ow);
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""GPU tests of the reference-facing operators: the three drop-in functions, their unfused kernels, autograd
+wiring, and the reference's rotation-dropout golden vectors replayed on the device."""
+import os
+
+import numpy as np
+import pytest
+
+from loans_b200 import workloads as W
+from oracle import stn_c as oc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _t(T, a, grad=False):
+    t = T.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_() if grad else t
+
+
+def test_rotation_dropout_reference_golden_on_device(T):
+    import loans_b200
+    from loans_b200.functions import RotationDropout, rotation_dropout
+    g = np.load(os.path.join(GOLDEN, "rotation_dropout.npz"))
+    for i in range(int(g["n_cases"])):
+        p = "c%03d_" % i
+        train, ratio, seed = g[p + "meta"]
+        with loans_b200.using_config("train", bool(train)):
+            np.random.seed(int(seed))                 # the reference draws from numpy's global stream
+            theta = _t(T, g[p + "theta"], grad=True)
+            node = RotationDropout(ratio)
+            y = node(theta)
+            assert np.array_equal(y.detach().cpu().numpy(), g[p + "y"]), i
+            if train:
+                y.backward(_t(T, g[p + "gy"]))
+                assert np.array_equal(theta.grad.cpu().numpy(), g[p + "gtheta"]), i
+            else:
+                with pytest.raises(AttributeError):     # reference :47-48 after a test-mode forward
+                    y.backward(_t(T, g[p + "gy"]))
+            np.random.seed(int(seed))
+            assert np.array_equal(rotation_dropout(theta.detach(), ratio=ratio).cpu().numpy(), g[p + "y"])
+
+
+def test_unfused_grid_and_sampler_kernels(T):
+    from tests import gpu_util as G
+    from loans_b200 import _lib
+    rng = np.random.default_rng(8)
+    b, c, h, w, oh, ow = 5, 3, 37, 29, 11, 14
+    x = rng.random((b, c, h, w), dtype=np.float32)
+    theta = W.make_theta(rng, b)
+    L = _lib.lib()
+    td = G.dev(theta)
+    grid = T.empty((b, 2, oh, ow), device="cuda")
+    _lib.check(L.loans_stn_grid_fwd(G.ptr(td), G.ptr(grid), b, oh, ow, G.stream()), "grid_fwd")
+    grid0 = oc.grid_forward(theta, (oh, ow))
+    assert np.array_equal(grid.cpu().numpy(), grid0)
+    # arbitrary (non-affine) grid, reaching outside the frame
+    garb = rng.uniform(-1.25, 1.25, (b, 2, oh, ow)).astype(np.float32)
+    gy = rng.standard_normal((b, c, oh, ow), dtype=np.float32)
+    xd, gd, gyd = G.dev(x), G.dev(garb), G.dev(gy)
+    y = T.empty((b, c, oh, ow), device="cuda")
+    _lib.check(L.loans_stn_sampler_fwd(G.ptr(xd), G.ptr(gd), G.ptr(y), b, 1, c, h, w, oh, ow, 0, G.stream()), "sampler_fwd")
+    assert np.array_equal(y.cpu().numpy(), oc.sampler_forward(x, garb))
+    gx = T.full((b, c, h, w), float("nan"), device="cuda")
+    gg = T.empty((b, 2, oh, ow), device="cuda")
+    _lib.check(L.loans_stn_sampler_bwd(G.ptr(xd), G.ptr(gd), G.ptr(gyd), G.ptr(gx), G.ptr(gg), b, 1, c, h, w, oh, ow, 0,
+                                       G.stream()), "sampler_bwd")
+    gx0, gg0 = oc.sampler_backward(x, garb, gy)
+    assert np.array_equal(gg.cpu().numpy(), gg0)
+    assert G.rel_max(gx.cpu().numpy(), gx0) <= 1e-5          # float atomics: order-dependent last bits
+    gth = T.empty((b, 2, 3), device="cuda")
+    _lib.check(L.loans_stn_grid_bwd(G.ptr(gg), G.ptr(gth), b, oh, ow, G.stream()), "grid_bwd")
+    assert G.rel_max(gth.cpu().numpy(), oc.grid_backward(gg0)) <= 1e-5
+
+
+def test_sampler_bwd_warp_aggregation_on_upsampling(T):
+    # heavy up-sampling: many crop pixels of one warp hit the same source pixel
+    from tests import gpu_util as G
+    from loans_b200 import _lib
+    rng = np.random.default_rng(9)
+    b, c, h, w, oh, ow = 2, 3, 6, 5, 40, 48
+    x = rng.random((b, c, h, w), dtype=np.float32)
+    theta = np.tile(np.array([[0.4, 0.05, 0.1], [-0.03, 0.5, 0]], np.float32), (b, 1, 1))
+    grid = oc.grid_forward(theta, (oh, ow))
+    gy = rng.standard_normal((b, c, oh, ow), dtype=np.float32)
+    xd, gd, gyd = G.dev(x), G.dev(grid), G.dev(gy)
+    gx = T.full((b, c, h, w), float("nan"), device="cuda")
+    _lib.check(_lib.lib().loans_stn_sampler_bwd(G.ptr(xd), G.ptr(gd), G.ptr(gyd), G.ptr(gx), None, b, 1, c, h, w, oh, ow, 0,
+                                                G.stream()), "sampler_bwd")
+    gx0, _ = oc.sampler_backward(x, grid, gy)
+    assert G.rel_max(gx.cpu().numpy(), gx0) <= 1e-5
+
+
+def test_drop_in_three_call_sequence_matches_fused_and_oracle(T):
+    """The reference's call sequence (sheep/sheep_localizer.py:61-63) plus the corner regularisers' use of the
+    grid (common/utils.py:152-157), through autograd."""
+    from loans_b200.functions import rotation_dropout, spatial_transformer_grid, spatial_transformer_sampler, stn_crop
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=6, rotate=True)
+    osz = (wl.out_h, wl.out_w)
+    gy = _t(T, d["gy"])
+    images = _t(T, d["x"])                                   # raw array: never requires grad in LoANs
+
+    def corner_loss(points):
+        return (points[:, :, 0, 0].sum() * 0.5 + points[:, :, 0, -1].sum() * 0.25 - points[:, :, -1, 0].sum())
+
+    # (1) as the reference writes it
+    theta1 = _t(T, d["theta"].reshape(-1, 6), grad=True)
+    tp = rotation_dropout(theta1.reshape(-1, 2, 3), ratio=0.0)
+    points = spatial_transformer_grid(tp, osz)
+    rois = spatial_transformer_sampler(images, points)
+    ((rois * gy).sum() + corner_loss(points)).backward()
+    # (2) fused
+    theta2 = _t(T, d["theta"], grad=True)
+    rois2, points2 = stn_crop(images, theta2, osz, ratio=0.0)
+    ((rois2 * gy).sum() + corner_loss(points2)).backward()
+    assert T.equal(rois, rois2) and T.equal(points, points2)
+    g1 = theta1.grad.reshape(-1, 2, 3).cpu().numpy()
+    g2 = theta2.grad.cpu().numpy()
+    # (3) oracle
+    gg = np.zeros((6, 2) + osz, np.float32)
+    gg[:, :, 0, 0] = 0.5
+    gg[:, :, 0, -1] = 0.25
+    gg[:, :, -1, 0] = -1.0
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+    gt0, _, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], gg, 0.0)
+    assert np.array_equal(rois.detach().cpu().numpy(), y0) and np.array_equal(points.detach().cpu().numpy(), grid0)
+    sc = np.abs(gt0).max()
+    assert np.abs(g1 - gt0).max() <= 1e-4 * sc and np.abs(g2 - gt0).max() <= 1e-4 * sc
+    assert np.all(g1[:, 0, 1] == 0) and np.all(g1[:, 1, 0] == 0)           # ratio 0.0 cuts the rotation gradient
+
+
+def test_sampler_falls_back_to_explicit_grid_when_grid_was_modified(T):
+    from loans_b200.functions import spatial_transformer_grid, spatial_transformer_sampler
+    rng = np.random.default_rng(2)
+    x = rng.random((3, 3, 20, 20), dtype=np.float32)
+    theta = W.make_theta(rng, 3)
+    xt = _t(T, x, grad=True)
+    grid = spatial_transformer_grid(_t(T, theta), (7, 7))
+    grid2 = grid * 0.5                                                      # a different tensor: no origin note
+    y = spatial_transformer_sampler(xt, grid2)
+    g0 = oc.grid_forward(theta, (7, 7)) * np.float32(0.5)
+    assert np.array_equal(y.detach().cpu().numpy(), oc.sampler_forward(x, g0))
+    gy = rng.standard_normal((3, 3, 7, 7), dtype=np.float32)
+    y.backward(_t(T, gy))
+    gx0, _ = oc.sampler_backward(x, g0, gy)
+    assert np.abs(xt.grad.cpu().numpy() - gx0).max() <= 1e-5 * np.abs(gx0).max()
+    grid.mul_(0.5)                                                          # in-place edit: version counter moved
+    y3 = spatial_transformer_sampler(xt.detach(), grid)
+    assert np.array_equal(y3.cpu().numpy(), oc.sampler_forward(x, g0))
+
+
+def test_gx_only_when_frames_require_grad(T):
+    from loans_b200 import _lib
+    from loans_b200.functions import stn_crop
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=2)
+    th = _t(T, d["theta"], grad=True)
+    xg = _t(T, d["x"], grad=True)
+    rois, _ = stn_crop(xg, th, (75, 75))
+    rois.backward(_t(T, d["gy"]))
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], (75, 75), d["gy"])
+    assert np.abs(xg.grad.cpu().numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max()
+    n0 = _lib.launch_count()
+    rois, _ = stn_crop(_t(T, d["x"]), th, (75, 75))
+    rois.backward(_t(T, d["gy"]))
+    assert _lib.launch_count() - n0 == 2                     # one fused kernel per direction
+
+
+def test_type_checks_and_cpu_tensors_are_refused(T):
+    from loans_b200.functions import InvalidType, spatial_transformer_grid, spatial_transformer_sampler, stn_crop
+    with pytest.raises(RuntimeError):
+        stn_crop(T.zeros(1, 3, 8, 8), T.zeros(1, 2, 3), (4, 4))
+    x = T.zeros(2, 3, 8, 8, device="cuda")
+    with pytest.raises(InvalidType):
+        spatial_transformer_grid(T.zeros(2, 3, 2, device="cuda"), (4, 4))
+    with pytest.raises(InvalidType):
+        spatial_transformer_grid(T.zeros(2, 2, 3, device="cuda", dtype=T.float64), (4, 4))
+    with pytest.raises(InvalidType):
+        spatial_transformer_sampler(x, T.zeros(3, 2, 4, 4, device="cuda"))
+    with pytest.raises(InvalidType):
+        spatial_transformer_sampler(x, T.zeros(2, 3, 4, 4, device="cuda"))
+    with pytest.raises(ValueError):
+        spatial_transformer_sampler(x, T.zeros(2, 2, 4, 4, device="cuda"), use_cudnn=True)

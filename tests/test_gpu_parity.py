@@ -1,0 +1,194 @@
+"""GPU parity: the CUDA path behind the C ABI vs the CPU oracle, on the same seeded inputs.
+
+Bars (BASELINE.json north_star): forward crops within 1e-5 relative, theta / input gradients within 1e-4
+relative.  What is actually asserted is tighter wherever the arithmetic allows it:
+  * grid, crops (fp32) and the per-pixel grid gradient are BIT-EXACT against oracle/stn_oracle.c
+    (same float32 rounding sequence; the kernels use _rn intrinsics where numpy rounds);
+  * gx comes from a gather that adds the same products in a different order: <= 2e-6 of max|gx|;
+  * gtheta is a 4096..5625-term float32 reduction vs the oracle's float64 sum: <= 1e-4 of max|gtheta|.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from loans_b200 import workloads as W
+from oracle import stn_c as oc
+from oracle import stn_numpy as on
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+FWD_TOL = 1e-5      # north_star, forward
+GRAD_TOL = 1e-4     # north_star, gradients
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    from tests import gpu_util
+    return gpu_util
+
+
+def _full_check(G, x, theta, osz, mask=1.0, k=1, seed=0, with_up=True):
+    rng = np.random.default_rng(seed)
+    n, c = theta.shape[0], x.shape[1]
+    gy = rng.standard_normal((n, c) + tuple(osz), dtype=np.float32)
+    gg = rng.standard_normal((n, 2) + tuple(osz), dtype=np.float32) if with_up else None
+    y, grid = G.crop_fwd(x, theta, osz, mask, k)
+    gt, gx, ggo = G.crop_bwd(x, theta, osz, gy, gg, mask, k)
+    y0, grid0 = oc.crop_forward(x, theta, osz, mask, k)
+    gt0, gx0, gg0 = oc.crop_backward(x, theta, osz, gy, gg, mask, k)
+    assert np.array_equal(grid, grid0), "grid not bit-exact"
+    assert np.array_equal(y, y0), "crops not bit-exact (max diff %g)" % np.abs(y - y0).max()
+    assert np.array_equal(ggo, gg0), "ggrid not bit-exact"
+    assert not np.isnan(gx).any() and not np.isnan(gt).any()
+    assert G.rel_max(gx, gx0) <= 2e-6 <= GRAD_TOL, ("gx", G.rel_max(gx, gx0))
+    assert np.abs(gt - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max()), ("gtheta", np.abs(gt - gt0).max())
+    return y, grid, gt, gx
+
+
+@pytest.mark.parametrize("name,batch,mask", [
+    ("cfg1", None, 0.0), ("cfg1", None, 1.0),
+    ("cfg2", None, 1.0), ("cfg2", 16, 0.0),
+    ("cfg3", 8, 0.0), ("cfg3", 4, 0.5),
+    ("cfg4", 4, 0.0), ("cfg4", 2, 1.0),
+    ("cfg5", 32, 0.0),
+])
+def test_workloads_against_oracle(G, name, batch, mask):
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True)
+    _full_check(G, d["x"], d["theta"], (wl.out_h, wl.out_w), mask, wl.crops_per_frame)
+
+
+def test_numpy_restatement_agrees_too(G):
+    # the literal numpy restatement (BLAS order in the grid contraction): within the north-star bars
+    wl = W.WORKLOADS["cfg2"]
+    d = W.make_inputs(wl, batch=8)
+    osz = (wl.out_h, wl.out_w)
+    y, grid = G.crop_fwd(d["x"], d["theta"], osz)
+    gt, gx, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"])
+    y0, grid0 = on.crop_forward(d["x"], d["theta"], osz)
+    gt0, gx0, _ = on.crop_backward(d["x"], d["theta"], osz, d["gy"])
+    assert G.rel_max(grid, grid0) <= 2.5e-7
+    assert G.rel_max(y, y0) <= FWD_TOL
+    assert G.rel_max(gx, gx0) <= GRAD_TOL and G.rel_max(gt, gt0) <= GRAD_TOL
+
+
+def test_bf16_crops_are_the_rounded_fp32_result(G):
+    wl = W.WORKLOADS["cfg3"]
+    d = W.make_inputs(wl, batch=6)
+    osz = (wl.out_h, wl.out_w)
+    y, grid = G.crop_fwd(d["x"], d["theta"], osz, 0.0, 1, bf16=True)
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+    assert np.array_equal(grid, grid0)
+    assert np.array_equal(y, G.bf16_round(y0))
+    # backward consumes bf16 gy: identical to the oracle fed the same rounded gy
+    gyr = G.bf16_round(d["gy"])
+    gt, gx, ggo = G.crop_bwd(d["x"], d["theta"], osz, gyr, None, 0.0, 1, bf16=True)
+    gt0, gx0, gg0 = oc.crop_backward(d["x"], d["theta"], osz, gyr, None, 0.0)
+    assert np.array_equal(ggo, gg0)
+    assert G.rel_max(gx, gx0) <= 2e-6 and G.rel_max(gt, gt0) <= GRAD_TOL
+
+
+HARD_THETAS = {
+    "identity": [[1, 0, 0], [0, 1, 0]],
+    "flip_x": [[-0.8, 0, 0.1], [0, 0.7, 0]],
+    "flip_both": [[-0.6, 0, 0], [0, -0.9, 0.05]],
+    "rot90": [[0, 0.8, 0], [-0.8, 0, 0]],
+    "rot45": [[0.5, -0.5, 0.1], [0.5, 0.5, -0.1]],
+    "shear": [[0.7, 0.6, 0], [0, 0.5, 0]],
+    "singular_rank1": [[0.5, 0.25, 0], [1.0, 0.5, 0.1]],
+    "zero": [[0, 0, 0.2], [0, 0, -0.3]],
+    "zero_x_only": [[0, 0, 0.2], [0, 0.8, 0]],
+    "upsample_8x": [[0.05, 0.01, 0.3], [-0.01, 0.06, -0.2]],
+    "huge_scale": [[40.0, 3.0, 0.5], [-2.0, 55.0, 0.1]],
+    "far_outside": [[0.5, 0, 7.0], [0, 0.5, -9.0]],
+    "half_outside": [[0.9, 0.1, 0.8], [0.05, 0.9, -0.7]],
+}
+
+
+@pytest.mark.parametrize("shape", [(3, 24, 24, 9, 9), (2, 17, 31, 12, 7), (1, 8, 8, 16, 16), (3, 20, 12, 1, 5),
+                                   (4, 13, 9, 6, 1), (5, 33, 45, 20, 30)])
+def test_hard_transforms_and_ragged_shapes(G, shape):
+    c, h, w, oh, ow = shape
+    names = sorted(HARD_THETAS)
+    theta = np.array([HARD_THETAS[nm] for nm in names], np.float32)
+    rng = np.random.default_rng(sum(shape))
+    x = rng.random((len(names), c, h, w), dtype=np.float32)
+    _full_check(G, x, theta, (oh, ow), 1.0, 1, seed=5)
+
+
+def test_identity_reproduces_full_size_frames(G):
+    # size-independent property at BASELINE config 3's frame size
+    x = np.random.default_rng(0).random((4, 3, 512, 512), dtype=np.float32)
+    theta = np.tile(np.array([[1, 0, 0], [0, 1, 0]], np.float32), (4, 1, 1))
+    y, _ = G.crop_fwd(x, theta, (512, 512))
+    assert np.array_equal(y, x)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4"])
+def test_full_size_adjoint_and_determinism(G, name):
+    """<crop(x), gy> == <x, gx> (the gather really is the transpose of the sampler), at full size; and the
+    fused path is bit-reproducible run to run (no atomics anywhere in it)."""
+    import torch
+    wl = W.WORKLOADS[name]
+    batch = 64 if name == "cfg3" else 32
+    d = W.make_inputs(wl, batch=batch, rotate=False)
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    y, _ = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k, want_grid=False)
+    gt, gx, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], None, 0.0, k, want_ggrid=False)
+    lhs = float((y.astype(np.float64) * d["gy"]).sum())
+    rhs = float((d["x"].astype(np.float64) * gx).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-3, (lhs, rhs)
+    gt2, gx2, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], None, 0.0, k, want_ggrid=False)
+    assert np.array_equal(gx, gx2) and np.array_equal(gt, gt2)
+    # oracle spot check on the first frames
+    nb = 2
+    gt0, gx0, _ = oc.crop_backward(d["x"][:nb], d["theta"][:nb * k], osz, d["gy"][:nb * k], None, 0.0, k)
+    assert G.rel_max(gx[:nb], gx0) <= 2e-6 and G.rel_max(gt[:nb * k], gt0) <= GRAD_TOL
+
+
+def test_shard_invariance_on_device(G):
+    wl = W.WORKLOADS["cfg5"]
+    d = W.make_inputs(wl, batch=16)
+    osz = (wl.out_h, wl.out_w)
+    y, grid = G.crop_fwd(d["x"], d["theta"], osz, 0.0)
+    gt, gx, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], None, 0.0)
+    for lo, hi in ((0, 8), (8, 16)):
+        ys, gs = G.crop_fwd(d["x"][lo:hi], d["theta"][lo:hi], osz, 0.0)
+        gts, gxs, _ = G.crop_bwd(d["x"][lo:hi], d["theta"][lo:hi], osz, d["gy"][lo:hi], None, 0.0)
+        assert np.array_equal(ys, y[lo:hi]) and np.array_equal(gs, grid[lo:hi])
+        assert np.array_equal(gts, gt[lo:hi]) and np.array_equal(gxs, gx[lo:hi])
+
+
+def test_optional_outputs_and_empty_batch(G):
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=3)
+    osz = (wl.out_h, wl.out_w)
+    y, grid = G.crop_fwd(d["x"], d["theta"], osz, 1.0, 1, want_grid=False)
+    assert grid is None
+    y0, _ = oc.crop_forward(d["x"], d["theta"], osz)
+    assert np.array_equal(y, y0)
+    gt, gx, ggo = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], None, 1.0, 1, need_gx=False, want_ggrid=False)
+    assert gx is None and ggo is None
+    gt0, _, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"])
+    assert np.abs(gt - gt0).max() <= GRAD_TOL * np.abs(gt0).max()
+    # empty batch: nothing launched, nothing touched
+    e = G.crop_fwd(np.zeros((0, 3, 8, 8), np.float32), np.zeros((0, 2, 3), np.float32), (4, 4))
+    assert e[0].shape == (0, 3, 4, 4)
+
+
+def test_golden_fixture_on_device(G):
+    g = np.load(os.path.join(GOLDEN, "stn_small.npz"))
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        osz = tuple(int(v) for v in g[p + "out_size"])
+        mask = float(g[p + "mask"])
+        y, grid = G.crop_fwd(g[p + "x"], g[p + "theta"], osz, mask)
+        gt, gx, ggo = G.crop_bwd(g[p + "x"], g[p + "theta"], osz, g[p + "gy"], g[p + "ggrid_up"], mask)
+        assert np.array_equal(y, g[p + "y"]) and np.array_equal(grid, g[p + "grid"])
+        assert np.array_equal(ggo, g[p + "ggrid"])
+        assert G.rel_max(gx, g[p + "gx"]) <= 2e-6 and G.rel_max(gt, g[p + "gtheta"]) <= GRAD_TOL

@@ -1,0 +1,138 @@
+"""CPU emulation of the kernels' per-pixel device code (loans_b200/csrc/stn_math.cuh) against the oracle.
+
+The header is compiled for the host with g++ -ffp-contract=off and driven pixel by pixel by
+tests/hostemu/stn_hostemu.cpp.  This checks, without a GPU, the float32 rounding chain of the forward, the
+per-pixel backward and -- the delicate part -- the inverse-mapping gather that produces gx, including
+rotations, flips, singular and wildly scaled transforms.  It is a test harness, not a product path.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from loans_b200 import workloads as W
+from oracle import stn_c as oc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostemu", "stn_hostemu.cpp")
+SO = os.path.join(HERE, "hostemu", "libstn_hostemu.so")
+_f = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    hdr = os.path.join(HERE, "..", "loans_b200", "csrc", "stn_math.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                        "-Wl,--unresolved-symbols=ignore-all", "-o", SO, SRC], check=True)
+    lib = ctypes.CDLL(SO)
+    lib.emu_crop_fwd.argtypes = [_f, _f, ctypes.c_float, _f, _f] + [ctypes.c_int] * 7
+    lib.emu_crop_bwd.argtypes = [_f, _f, ctypes.c_float, _f, _f, _f, _f, _f] + [ctypes.c_int] * 7
+    lib.emu_crop_fwd.restype = lib.emu_crop_bwd.restype = None
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_f)
+
+
+def run_emu(lib, x, theta, osz, gy, gg, mask, k):
+    b, c, h, w = x.shape
+    n = theta.shape[0]
+    oh, ow = osz
+    y = np.empty((n, c, oh, ow), np.float32)
+    grid = np.empty((n, 2, oh, ow), np.float32)
+    lib.emu_crop_fwd(_p(x), _p(theta), mask, _p(y), _p(grid), n, k, c, h, w, oh, ow)
+    gt = np.empty((n, 2, 3), np.float32)
+    gx = np.full_like(x, np.nan)
+    ggo = np.empty_like(grid)
+    lib.emu_crop_bwd(_p(x), _p(theta), mask, _p(gy), _p(gg), _p(gt), _p(gx), _p(ggo), n, k, c, h, w, oh, ow)
+    return y, grid, gt, gx, ggo
+
+
+def check(lib, x, theta, osz, mask=1.0, k=1, seed=0):
+    rng = np.random.default_rng(seed)
+    n, c = theta.shape[0], x.shape[1]
+    gy = rng.standard_normal((n, c) + tuple(osz), dtype=np.float32)
+    gg = rng.standard_normal((n, 2) + tuple(osz), dtype=np.float32)
+    y, grid, gt, gx, ggo = run_emu(lib, x, theta, osz, gy, gg, mask, k)
+    y0, grid0 = oc.crop_forward(x, theta, osz, mask, k)
+    gt0, gx0, gg0 = oc.crop_backward(x, theta, osz, gy, gg, mask, k)
+    assert np.array_equal(grid, grid0), "grid not bit-exact"
+    assert np.array_equal(y, y0), "crop not bit-exact"
+    assert np.array_equal(ggo, gg0), "ggrid not bit-exact"
+    assert not np.isnan(gx).any()
+    sc = max(1.0, float(np.abs(gx0).max()))
+    assert np.abs(gx - gx0).max() <= 2e-6 * sc, ("gx", np.abs(gx - gx0).max(), sc)
+    sc = max(1.0, float(np.abs(gt0).max()))
+    assert np.abs(gt - gt0).max() <= 1e-4 * sc, ("gtheta", np.abs(gt - gt0).max(), sc)
+
+
+@pytest.mark.parametrize("wl,batch,mask", [("cfg2", 3, 1.0), ("cfg1", 2, 0.0), ("cfg3", 1, 0.0), ("cfg4", 1, 0.0)])
+def test_workload_shapes(emu, wl, batch, mask):
+    wl = W.WORKLOADS[wl]
+    d = W.make_inputs(wl, batch=batch, rotate=True)
+    check(emu, d["x"], d["theta"], (wl.out_h, wl.out_w), mask, wl.crops_per_frame)
+
+
+def _theta(rows):
+    return np.array(rows, np.float32).reshape(-1, 2, 3)
+
+
+HARD_THETAS = {
+    "identity": [[1, 0, 0], [0, 1, 0]],
+    "flip_x": [[-0.8, 0, 0.1], [0, 0.7, 0]],
+    "flip_both": [[-0.6, 0, 0], [0, -0.9, 0.05]],
+    "rot90": [[0, 0.8, 0], [-0.8, 0, 0]],
+    "rot45": [[0.5, -0.5, 0.1], [0.5, 0.5, -0.1]],
+    "shear": [[0.7, 0.6, 0], [0, 0.5, 0]],
+    "singular_rank1": [[0.5, 0.25, 0], [1.0, 0.5, 0.1]],
+    "zero": [[0, 0, 0.2], [0, 0, -0.3]],
+    "zero_x_only": [[0, 0, 0.2], [0, 0.8, 0]],
+    "point_on_pixel": [[0, 0, 0], [0, 0, 0]],
+    "upsample_8x": [[0.05, 0.01, 0.3], [-0.01, 0.06, -0.2]],
+    "huge_scale": [[40.0, 3.0, 0.5], [-2.0, 55.0, 0.1]],
+    "far_outside": [[0.5, 0, 7.0], [0, 0.5, -9.0]],
+    "edge_exact": [[1.0, 0, 2.0 / 23.0], [0, 1.0, 0]],
+    "tiny_rotation": [[0.8, 1e-7, 0], [-1e-7, 0.8, 0]],
+    "half_outside": [[0.9, 0.1, 0.8], [0.05, 0.9, -0.7]],
+}
+
+
+@pytest.mark.parametrize("name", sorted(HARD_THETAS))
+@pytest.mark.parametrize("shape", [(24, 24, 9, 9), (17, 31, 12, 7), (8, 8, 16, 16), (20, 12, 1, 5), (13, 9, 6, 1)])
+def test_hard_transforms(emu, name, shape):
+    h, w, oh, ow = shape
+    rng = np.random.default_rng(abs(hash((name, shape))) % (2 ** 31))
+    x = rng.random((1, 2, h, w), dtype=np.float32)
+    check(emu, x, _theta([HARD_THETAS[name]]), (oh, ow), 1.0, 1, seed=3)
+
+
+def test_random_transforms_many(emu):
+    rng = np.random.default_rng(99)
+    for it in range(60):
+        h, w = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+        oh, ow = int(rng.integers(1, 24)), int(rng.integers(1, 24))
+        k = int(rng.integers(1, 4))
+        b = int(rng.integers(1, 3))
+        c = int(rng.integers(1, 5))
+        x = rng.random((b, c, h, w), dtype=np.float32)
+        theta = rng.uniform(-1.5, 1.5, (b * k, 2, 3)).astype(np.float32)
+        if it % 3 == 0:
+            theta[:, :, :2] *= rng.uniform(0.01, 0.3)
+        mask = [1.0, 0.0, 0.5][it % 3]
+        check(emu, x, theta, (oh, ow), mask, k, seed=it)
+
+
+def test_golden_fixture(emu):
+    g = np.load(os.path.join(HERE, "golden", "stn_small.npz"))
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        osz = tuple(int(v) for v in g[p + "out_size"])
+        y, grid, gt, gx, ggo = run_emu(emu, g[p + "x"], g[p + "theta"], osz, g[p + "gy"], g[p + "ggrid_up"],
+                                       float(g[p + "mask"]), 1)
+        assert np.array_equal(y, g[p + "y"]) and np.array_equal(grid, g[p + "grid"]) and np.array_equal(ggo, g[p + "ggrid"])
+        assert np.abs(gx - g[p + "gx"]).max() <= 2e-6 * max(1.0, np.abs(g[p + "gx"]).max())
+        assert np.abs(gt - g[p + "gtheta"]).max() <= 1e-4 * max(1.0, np.abs(g[p + "gtheta"]).max())
