@@ -7,15 +7,20 @@
 //   if asked, the grid -- a required output of the reference API -- from the same registers.
 //
 // Backward (stn_bwd_kernel): one launch, two CTA roles.
-//   * theta role, CTAs [0, theta_ctas): a thread-block CLUSTER per crop.  Each CTA walks its share of the
-//     crop pixels (taps + gy -> d/du, d/dv, plus the upstream grid gradient), reduces the six sums of
-//     gtheta = ggrid . [xs; ys; 1]^T with warp shuffles and shared memory, and rank 0 of the cluster adds
-//     the per-CTA partials through distributed shared memory in a fixed order: deterministic, no atomics,
-//     no zero-initialised output, no workspace.
-//   * gx role, the remaining CTAs: the image gradient as a GATHER.  Each thread owns one frame pixel,
-//     inverts the affine map to find the few crop pixels whose 2x2 taps cover it (stn_math.cuh), and
-//     writes the dense gx exactly once with coalesced stores, zeros included -- no memset pass, no float
-//     atomics, bit-reproducible.  With K crops per frame the K contributions are summed in registers.
+//   * gx role, CTAs [0, gx_ctas) (scheduled first: the long pole).  A CTA owns a tile of frame pixels in shared
+//     memory.  For every crop of that frame it walks the crop pixels whose 2x2 tap window can touch the tile
+//     (found by inverting the affine map), re-evaluates each with the exact forward chain and adds
+//     gy * wu * wv into the tile.  Crop pixels are processed in P*Q conflict-free phases (stn_math.cuh:
+//     ScatterGeom) so the adds are plain shared-memory read-modify-writes: no atomics, fixed summation order,
+//     bit-reproducible.  The tile -- zeros included -- is then written to gx exactly once with coalesced
+//     128-bit stores: no memset pass.  Work is proportional to the number of CROP pixels, not frame pixels.
+//     Degenerate transforms (singular / extreme up-sampling) fall back, per crop, to an exact per-frame-pixel
+//     gather at write-out time.
+//   * theta role, the remaining CTAs: a thread-block CLUSTER per crop.  Each CTA walks its share of the crop
+//     pixels (taps + gy -> d/du, d/dv, plus the upstream grid gradient), reduces the six sums of
+//     gtheta = ggrid . [xs; ys; 1]^T with warp shuffles and shared memory, and rank 0 of the cluster adds the
+//     per-CTA partials through distributed shared memory in a fixed order: deterministic, no atomics, no
+//     zero-initialised output, no workspace.
 #include <cooperative_groups.h>
 
 #include "stn_common.cuh"
@@ -23,6 +28,24 @@
 namespace cg = cooperative_groups;
 
 namespace stn {
+
+// per-thread walk over a CTA's share of the crop pixels without divisions in the loop
+struct PxWalk {
+    int q, i, j;
+    int di, dj, ow;
+    __device__ __forceinline__ PxWalk(int q0, int ow_) : q(q0), ow(ow_)
+    {
+        i = q0 / ow_;
+        j = q0 - i * ow_;
+        di = kThreads / ow_;
+        dj = kThreads - di * ow_;
+    }
+    __device__ __forceinline__ void next()
+    {
+        q += kThreads; i += di; j += dj;
+        if (j >= ow) { j -= ow; ++i; }
+    }
+};
 
 // ------------------------------------------------------------------------------------------ forward
 template <typename YT, int CG, bool FROM_GRID>
@@ -40,39 +63,41 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const CropParams p)
     const int q_end = min(npx, (tile + 1) * p.px_per_cta);
     Theta th = {};
     if (!FROM_GRID) th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
-    const size_t plane = (size_t)p.H * p.W;
+    const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * p.C * plane;
     YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * p.C * npx;
-    const size_t gbase = (size_t)n * 2 * npx;
+    float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
+    const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
 
-    for (int q = tile * p.px_per_cta + threadIdx.x; q < q_end; q += kThreads) {
+    for (PxWalk w(tile * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
         float g0, g1;
         if (FROM_GRID) {
-            g0 = __ldg(p.grid_in + gbase + q);
-            g1 = __ldg(p.grid_in + gbase + npx + q);
+            g0 = __ldg(gin + w.q);
+            g1 = __ldg(gin + npx + w.q);
         } else {
-            const int i = q / p.oW, j = q - i * p.oW;
-            const float xsj = xs[j], ysi = ys[i];
+            const float xsj = xs[w.j], ysi = ys[w.i];
             g0 = grid_elem(th.t00, th.t01, th.t02, xsj, ysi);
             g1 = grid_elem(th.t10, th.t11, th.t12, xsj, ysi);
-            if (p.grid_out) {
-                p.grid_out[gbase + q] = g0;
-                p.grid_out[gbase + npx + q] = g1;
+            if (gout) {
+                gout[w.q] = g0;
+                gout[npx + w.q] = g1;
             }
         }
         const Tap t = make_tap(g0, g1, p.H, p.W);
         const TapAddr a = make_tap_addr(t, p.H, p.W);
-        const Weights4 w = make_weights(t);
+        const Weights4 wt = make_weights(t);
+        const float *xc = xb;
+        YT *yc = yb + w.q;
         for (int c0 = 0; c0 < p.C; c0 += CG) {
             float v[CG][4];
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C)
-                    load_taps(xb + (size_t)(c0 + ch) * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                if (c0 + ch < p.C) load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C)
-                    Elem<YT>::store(yb, (size_t)(c0 + ch) * npx + q, interp(w, v[ch][0], v[ch][1], v[ch][2], v[ch][3]));
+                if (c0 + ch < p.C) Elem<YT>::store(yc, ch * npx, interp(wt, v[ch][0], v[ch][1], v[ch][2], v[ch][3]));
+            xc += CG * plane;
+            yc += CG * npx;
         }
     }
 }
@@ -88,37 +113,40 @@ __device__ __forceinline__ float warp_sum(float v)
 struct BwdSmem {
     float red[kWarps][6];
     float part[6];        // this CTA's partial gtheta sums, read by cluster rank 0 through DSMEM
+    int flags[2];
 };
 
 template <typename GT, int CG>
-__device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm)
+__device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
 {
     const int cs = p.ctas_per_crop;
-    const int n = blockIdx.x / cs;
-    const int rank = blockIdx.x - n * cs;
+    const int n = cta / cs;
+    const int rank = cta - n * cs;
     const int npx = p.oH * p.oW;
     const int q_end = min(npx, (rank + 1) * p.px_per_cta);
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
-    const size_t plane = (size_t)p.H * p.W;
+    const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * p.C * plane;
     const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * p.C * npx;
-    const size_t gbase = (size_t)n * 2 * npx;
+    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
+    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
 
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int q = rank * p.px_per_cta + threadIdx.x; q < q_end; q += kThreads) {
-        const int i = q / p.oW, j = q - i * p.oW;
-        const float xsj = xs[j], ysi = ys[i];
+    for (PxWalk w(rank * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
+        const float xsj = xs[w.j], ysi = ys[w.i];
         const Tap t = make_tap(grid_elem(th.t00, th.t01, th.t02, xsj, ysi),
                                grid_elem(th.t10, th.t11, th.t12, xsj, ysi), p.H, p.W);
         const TapAddr a = make_tap_addr(t, p.H, p.W);
         float su = 0.f, sv = 0.f;
+        const float *xc = xb;
+        const GT *gc = gyb + w.q;
         for (int c0 = 0; c0 < p.C; c0 += CG) {
             float v[CG][4], g[CG];
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
                 if (c0 + ch < p.C) {
-                    load_taps(xb + (size_t)(c0 + ch) * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-                    g[ch] = Elem<GT>::load(gyb, (size_t)(c0 + ch) * npx + q);
+                    load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                    g[ch] = Elem<GT>::load(gc, ch * npx);
                 }
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
@@ -130,15 +158,17 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
                     if (c0 + ch == 0) { su = gu; sv = gv; }
                     else { su = f_add(su, gu); sv = f_add(sv, gv); }          // numpy.sum over the channel axis
                 }
+            xc += CG * plane;
+            gc += CG * npx;
         }
         finish_grad_uv(t, p.H, p.W, su, sv);
-        if (p.ggrid_out) {
-            p.ggrid_out[gbase + q] = su;
-            p.ggrid_out[gbase + npx + q] = sv;
+        if (ggo) {
+            ggo[w.q] = su;
+            ggo[npx + w.q] = sv;
         }
-        if (p.ggrid_up) {
-            su = f_add(su, __ldg(p.ggrid_up + gbase + q));
-            sv = f_add(sv, __ldg(p.ggrid_up + gbase + npx + q));
+        if (ggu) {
+            su = f_add(su, __ldg(ggu + w.q));
+            sv = f_add(sv, __ldg(ggu + npx + w.q));
         }
         s[0] = fmaf(su, xsj, s[0]); s[1] = fmaf(su, ysi, s[1]); s[2] += su;
         s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
@@ -180,60 +210,165 @@ struct GyLoader {
     __device__ __forceinline__ float operator()(const GT *p, size_t i) const { return Elem<GT>::load(p, i); }
 };
 
+// Scalar write-out of a tile, plus -- for crops whose transform is too degenerate for the phased scatter -- their
+// contribution gathered per frame pixel (exact, slow, rare).  Kept out of line so that it does not weigh on the
+// register allocation of the fast path.
 template <typename GT, int CG>
-__device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, InvCrop *inv)
+__device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys,
+                                              const ScatterGeom *geom, const InvCrop *inv, const float *tile,
+                                              float *gxb, const GT *gy, int b, int c0, int nc,
+                                              int r0, int tr, int s0, int tw, bool any_fallback)
 {
-    const int gx_ctas = (int)gridDim.x - p.theta_ctas;
-    const int me = (int)blockIdx.x - p.theta_ctas;
-    const int B = p.N / p.K;
-    const int total = B * p.gx_tiles_per_frame;
-    const int per = (total + gx_ctas - 1) / gx_ctas;       // contiguous tile range: few frame switches per CTA
-    const int t_begin = me * per, t_end = min(total, t_begin + per);
+    const int twp = p.gx_tile_pitch, tile_plane = p.gx_tile_rows * twp;
     const int npx = p.oH * p.oW, fpx = p.H * p.W;
-    const GT *gy = reinterpret_cast<const GT *>(p.gy);
-    int cur_b = -1;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b = tile / p.gx_tiles_per_frame;
-        const int chunk = tile - b * p.gx_tiles_per_frame;
-        if (b != cur_b) {
-            __syncthreads();
-            for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
-                inv[kk] = make_inv_crop(load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01),
-                                        p.H, p.W, p.oH, p.oW);
-            __syncthreads();
-            cur_b = b;
-        }
-        const int q_end = min(fpx, (chunk + 1) * p.gx_tile_px);
-        for (int q = chunk * p.gx_tile_px + threadIdx.x; q < q_end; q += kThreads) {
-            const int r = q / p.W, s = q - r * p.W;
-            for (int c0 = 0; c0 < p.C; c0 += CG) {
-                const int nc = min(CG, p.C - c0);
-                float acc[CG];
+    for (int e = threadIdx.x; e < tr * tw; e += kThreads) {
+        const int row = e / tw, col = e - row * tw;
+        float acc[CG];
 #pragma unroll
-                for (int ch = 0; ch < CG; ++ch) acc[ch] = 0.f;
-                for (int kk = 0; kk < p.K; ++kk)
-                    gather_from_crop<CG>(inv[kk], xs, ys, p.H, p.W, p.oH, p.oW, r + 1, s + 1,
+        for (int ch = 0; ch < CG; ++ch) acc[ch] = ch < nc ? tile[ch * tile_plane + row * twp + col] : 0.f;
+        if (any_fallback)
+            for (int kk = 0; kk < p.K; ++kk)
+                if (geom[kk].P == 0)
+                    gather_from_crop<CG>(inv[kk], xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
                                          gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx, nc, GyLoader<GT>(), acc);
 #pragma unroll
-                for (int ch = 0; ch < CG; ++ch)
-                    if (ch < nc) p.gx[((size_t)b * p.C + c0 + ch) * fpx + q] = acc[ch];
-            }
+        for (int ch = 0; ch < CG; ++ch)
+            if (ch < nc) gxb[(size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + col] = acc[ch];
+    }
+}
+
+__device__ __noinline__ void fill_inv_crop(InvCrop *dst, Theta th, int H, int W, int oH, int oW)
+{
+    *dst = make_inv_crop(th, H, W, oH, oW);
+}
+
+// one crop pixel of the scatter: exact forward chain, then up to 4 taps x nc channels added into the tile
+template <typename GT, int CG>
+__device__ __forceinline__ void scatter_pixel(const CropParams &p, const Theta &th, float xsj, float ysi,
+                                              const GT *gy_px, int nc, int npx,
+                                              float *tile, int tile_plane, int twp, int r0, int tr, int s0, int tw)
+{
+    ScatterTaps st;
+    if (!scatter_taps(th, xsj, ysi, p.H, p.W, r0, tr, s0, tw, st)) return;
+    const Tap &t = st.t;
+    const int row0 = st.row0, col0 = st.col0;
+    const bool rv0 = st.rv0, rv1 = st.rv1, cv0 = st.cv0, cv1 = st.cv1;
+    float g[CG];
+#pragma unroll
+    for (int ch = 0; ch < CG; ++ch)
+        if (ch < nc) g[ch] = Elem<GT>::load(gy_px, ch * npx);
+    float *t00 = tile + row0 * twp + col0;
+#pragma unroll
+    for (int ch = 0; ch < CG; ++ch)
+        if (ch < nc) {
+            float *tc = t00 + ch * tile_plane;
+            const float a1 = f_mul(g[ch], t.wu1), a0 = f_mul(g[ch], t.wu0);      // gy * wu * wv, reference order
+            if (rv0 && cv0) tc[0] = f_add(tc[0], f_mul(a1, t.wv1));
+            if (rv0 && cv1) tc[1] = f_add(tc[1], f_mul(a0, t.wv1));
+            if (rv1 && cv0) tc[twp] = f_add(tc[twp], f_mul(a1, t.wv0));
+            if (rv1 && cv1) tc[twp + 1] = f_add(tc[twp + 1], f_mul(a0, t.wv0));
         }
+}
+
+template <typename GT, int CG>
+__device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm,
+                                        ScatterGeom *geom, InvCrop *inv, float *tile)
+{
+    const int tiles_x = p.gx_tiles_x, tiles_per_frame = p.gx_tiles_per_frame;
+    const int b = blockIdx.x / tiles_per_frame;
+    const int tix = blockIdx.x - b * tiles_per_frame;
+    const int ty = tix / tiles_x, tx = tix - ty * tiles_x;
+    const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
+    const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
+    const int twp = p.gx_tile_pitch;
+    const int tile_plane = p.gx_tile_rows * twp;
+    const int npx = p.oH * p.oW, fpx = p.H * p.W;
+    const GT *gy = reinterpret_cast<const GT *>(p.gy);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // per-crop geometry of this frame (float32, conservative) -- and whether any crop needs the gather fallback
+    if (threadIdx.x == 0) sm.flags[0] = 0;
+    __syncthreads();
+    for (int kk = threadIdx.x; kk < p.K; kk += kThreads) {
+        const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
+        geom[kk] = make_scatter_geom(th, p.H, p.W, p.oH, p.oW);
+        if (geom[kk].P == 0) {
+            fill_inv_crop(&inv[kk], th, p.H, p.W, p.oH, p.oW);
+            sm.flags[0] = 1;
+        }
+    }
+    __syncthreads();
+    const bool any_fallback = sm.flags[0] != 0;
+
+    for (int c0 = 0; c0 < p.C; c0 += CG) {
+        const int nc = min(CG, p.C - c0);
+        {   // zero the tile
+            float4 *t4 = reinterpret_cast<float4 *>(tile);
+            const int n4 = CG * tile_plane / 4;
+            for (int e = threadIdx.x; e < n4; e += kThreads) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        for (int kk = 0; kk < p.K; ++kk) {
+            const ScatterGeom &g = geom[kk];
+            if (g.P == 0) continue;                                            // CTA-uniform
+            int i_lo, i_hi, j_lo, j_hi;
+            if (!scatter_box(g, r0, tr, s0, tw, p.oH, p.oW, i_lo, i_hi, j_lo, j_hi)) continue;   // CTA-uniform
+            const GT *gyc = gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx;
+            const Theta th = g.th;
+            const int P = g.P, Q = g.Q;
+            for (int cp = 0; cp < P; ++cp)
+                for (int cq = 0; cq < Q; ++cq) {
+                    // rows i == cp (mod P) are dealt to the warps, columns j == cq (mod Q) to the lanes
+                    const int ia = first_congruent(i_lo, cp, P), ja = first_congruent(j_lo, cq, Q);
+                    for (int i = ia + warp * P; i <= i_hi; i += kWarps * P) {
+                        const float ysi = ys[i];
+                        for (int j = ja + lane * Q; j <= j_hi; j += 32 * Q) {
+                            if (!scatter_pretest(g, i, j, r0, tr, s0, tw)) continue;
+                            scatter_pixel<GT, CG>(p, th, xs[j], ysi, gyc + i * p.oW + j, nc, npx,
+                                                  tile, tile_plane, twp, r0, tr, s0, tw);
+                        }
+                    }
+                    __syncthreads();                                           // phase (and crop) boundary
+                }
+        }
+        // write the tile out: each gx element exactly once, zeros included
+        float *gxb = p.gx + ((size_t)b * p.C + c0) * fpx;
+        if (p.gx_vec4 && !any_fallback) {
+            const int tw4 = tw >> 2;                                           // tw % 4 == 0 guaranteed by the host
+            for (int ch = 0; ch < nc; ++ch)
+                for (int e = threadIdx.x; e < tr * tw4; e += kThreads) {
+                    const int row = e / tw4, c4 = e - row * tw4;
+                    const float4 v = *reinterpret_cast<const float4 *>(tile + ch * tile_plane + row * twp + 4 * c4);
+                    *reinterpret_cast<float4 *>(gxb + (size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + 4 * c4) = v;
+                }
+        } else {
+            gx_writeout_slow<GT, CG>(p, xs, ys, geom, inv, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
+        }
+        __syncthreads();
     }
 }
 
 template <typename GT, int CG>
-__global__ void __launch_bounds__(kThreads) stn_bwd_kernel(const CropParams p)
+__global__ void __launch_bounds__(kThreads, 3) stn_bwd_kernel(const CropParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
-    float *xs = reinterpret_cast<float *>(smem_raw + sizeof(BwdSmem));
+    // layout: [tile (gx role only, 16 B aligned)] [BwdSmem] [xs | ys] [ScatterGeom[K]] [InvCrop[K]]
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    unsigned char *q = smem_raw + p.gx_tile_bytes;
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(q);
+    q += sizeof(BwdSmem);
+    float *xs = reinterpret_cast<float *>(q);
     float *ys = xs + p.oW;
-    InvCrop *inv = reinterpret_cast<InvCrop *>(ys + p.oH + ((p.oW + p.oH) & 1));    // 8-byte aligned
+    q += sizeof(float) * ((p.oW + p.oH + 1) & ~1);
+    ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
+    InvCrop *inv = reinterpret_cast<InvCrop *>(q + sizeof(ScatterGeom) * (p.gx ? p.K : 0));
     fill_axis_tables(xs, ys, p.oW, p.oH, p.xstep, p.ystep);
     __syncthreads();
-    if ((int)blockIdx.x < p.theta_ctas) theta_role<GT, CG>(p, xs, ys, sm);
-    else gx_role<GT, CG>(p, xs, ys, inv);
+    if ((int)blockIdx.x < p.gx_ctas) {
+        if ((int)blockIdx.x < p.gx_tiles_total) gx_role<GT, CG>(p, xs, ys, sm, geom, inv, tile);
+    } else {
+        theta_role<GT, CG>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host launchers
@@ -281,9 +416,13 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
 template <typename GT, int CG>
 static cudaError_t launch_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
-    if (smem > 48 * 1024) {      // only very large crops-per-frame counts leave the default dynamic limit
-        cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+        static size_t granted = 0;                 // per template instance; only ever grows
+        if (smem > granted) {
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            granted = smem;
+        }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -314,6 +453,7 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
 {
     if (p.N == 0) return 0;
     const long long npx = (long long)p.oH * p.oW;
+    const int cgsel = pick_channel_group(p.C);
     // cluster size: enough theta-role CTAs to occupy the machine twice over, 8 (portable maximum) at most
     unsigned cs = 1;
     while (cs < 8 && (long long)p.N * cs < 2LL * kNumSMs && npx / (2 * cs) >= kThreads / 2) cs *= 2;
@@ -321,21 +461,33 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     p.px_per_cta = (int)((npx + cs - 1) / cs);
     const long long theta_ctas = (long long)p.N * cs;
     long long gx_ctas = 0;
+    size_t smem = sizeof(BwdSmem) + sizeof(float) * (size_t)((p.oW + p.oH + 1) & ~1);
     if (p.gx) {
-        const long long fpx = (long long)p.H * p.W;
-        p.gx_tile_px = 4 * kThreads;
-        p.gx_tiles_per_frame = (int)((fpx + p.gx_tile_px - 1) / p.gx_tile_px);
+        // tile: groups of full rows when they fit the budget, column chunks otherwise; pitch/width multiples of 4
+        const int budget = 40 * 1024 / (int)sizeof(float) / cgsel;               // floats per channel plane
+        int tw = p.W;
+        if ((long long)((p.W + 3) & ~3) * 2 > budget) { tw = (budget / 2) & ~3; if (tw < 4) tw = 4; }
+        const int twp = (tw + 3) & ~3;
+        int tr = budget / twp;
+        if (tr > 32) tr = 32;
+        if (tr > p.H) tr = p.H;
+        if (tr < 1) tr = 1;
+        p.gx_tile_rows = tr; p.gx_tile_cols = tw; p.gx_tile_pitch = twp;
+        p.gx_tiles_x = (p.W + tw - 1) / tw;
+        const int tiles_y = (p.H + tr - 1) / tr;
+        p.gx_tiles_per_frame = p.gx_tiles_x * tiles_y;
+        p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * twp);
+        p.gx_vec4 = (p.W % 4 == 0 && tw % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
         const long long tiles = (long long)(p.N / p.K) * p.gx_tiles_per_frame;
-        gx_ctas = tiles < 6LL * kNumSMs ? tiles : 6LL * kNumSMs;
-        gx_ctas = ((gx_ctas + cs - 1) / cs) * cs;
+        if (tiles > 0x3fffffffLL) return set_error("crop_bwd: too many gx tiles (%lld)", tiles);
+        p.gx_tiles_total = (int)tiles;
+        gx_ctas = ((tiles + cs - 1) / cs) * cs;                                 // cluster boundaries stay on role boundaries
+        smem += (size_t)p.gx_tile_bytes + (sizeof(ScatterGeom) + sizeof(InvCrop)) * (size_t)p.K;
     }
+    p.gx_ctas = (int)gx_ctas;
     const long long ctas = theta_ctas + gx_ctas;
     if (ctas > 0x7fffffffLL) return set_error("crop_bwd: too many CTAs (%lld)", ctas);
-    p.theta_ctas = (int)theta_ctas;
-    size_t smem = sizeof(BwdSmem) + sizeof(float) * (size_t)(p.oW + p.oH + 1);
-    if (p.gx) smem += sizeof(InvCrop) * (size_t)p.K;
     if (smem > 200 * 1024) return set_error("crop_bwd: %d crops per frame need %zu B of shared memory (max 200 KiB)", p.K, smem);
-    const int cgsel = pick_channel_group(p.C);
     cudaError_t e = gy_dtype == 0 ? launch_bwd_t<float>(p, cgsel, (unsigned)ctas, cs, smem, stream)
                                   : launch_bwd_t<__nv_bfloat16>(p, cgsel, (unsigned)ctas, cs, smem, stream);
     count_launch();

@@ -305,4 +305,110 @@ STN_HD void gather_from_crop(const InvCrop &c, const float *xs, const float *ys,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Geometry for the tile-scatter formulation of gx (the fast path; the gather above is its fallback).
+//
+// A CTA owns a tile of frame pixels in shared memory and adds into it the contributions of every crop pixel
+// whose 2x2 tap window touches the tile.  Two crop pixels can only touch the same frame pixel if their
+// coordinates differ by less than 2 in BOTH u and v; for an affine map that bounds their index distance by
+//   |dj| < Ej = (|i00|+|i01|)*T ,  |di| < Ei = (|i10|+|i11|)*T ,  T = 2 + margin.
+// Crop pixels are therefore processed in P*Q phases, (i mod P, j mod Q) = const per phase with P >= Ei,
+// Q >= Ej: inside one phase no two pixels share a frame pixel, so plain read-modify-writes are race free and
+// the summation order is fixed (deterministic).  Down-sampling by >= 2 gives P = Q = 1: a single phase.
+// Everything here is float32 and only needs to be CONSERVATIVE (it selects candidates and phases); every
+// candidate is re-evaluated with the exact forward chain before anything is added.
+struct ScatterGeom {
+    Theta th;
+    float muj, mui, cu, mvj, mvi, cv;   // approximate affine map (padded px) for the cheap pre-test
+    float i00, i01, i10, i11;           // its inverse
+    float slack;                        // pre-test slack in px
+    int P, Q;                           // phase periods; P == 0 -> use the gather fallback for this crop
+};
+
+constexpr int kMaxScatterPhases = 64;
+
+STN_HD ScatterGeom make_scatter_geom(const Theta &th, int H, int W, int oH, int oW)
+{
+    ScatterGeom g;
+    g.th = th;
+    const float sx = oW > 1 ? 2.0f / (float)(oW - 1) : 0.0f;
+    const float sy = oH > 1 ? 2.0f / (float)(oH - 1) : 0.0f;
+    const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
+    g.muj = th.t00 * sx * hw; g.mui = th.t01 * sy * hw; g.cu = (th.t02 - th.t00 - th.t01 + 1.0f) * hw + 1.0f;
+    g.mvj = th.t10 * sx * hh; g.mvi = th.t11 * sy * hh; g.cv = (th.t12 - th.t10 - th.t11 + 1.0f) * hh + 1.0f;
+    const float nj = (float)(oW > 1 ? oW - 1 : 1), ni = (float)(oH > 1 ? oH - 1 : 1);
+    const float mag = fabsf(g.muj) * nj + fabsf(g.mui) * ni + fabsf(g.cu) + fabsf(g.mvj) * nj + fabsf(g.mvi) * ni
+                    + fabsf(g.cv) + (float)(W + H);
+    g.slack = 0.05f + 1e-5f * mag;
+    const float det = g.muj * g.mvi - g.mui * g.mvj;
+    const float scale = fabsf(g.muj * g.mvi) + fabsf(g.mui * g.mvj);
+    g.P = 0; g.Q = 0;
+    g.i00 = g.i01 = g.i10 = g.i11 = 0.0f;
+    if (fabsf(det) > 1e-5f * scale + 1e-20f && mag < 1e6f) {
+        const float r = 1.0f / det;
+        g.i00 = g.mvi * r; g.i01 = -g.mui * r; g.i10 = -g.mvj * r; g.i11 = g.muj * r;
+        const float T = 2.0f + 2.0f * g.slack;
+        const float ej = (fabsf(g.i00) + fabsf(g.i01)) * T * 1.001f, ei = (fabsf(g.i10) + fabsf(g.i11)) * T * 1.001f;
+        if (ej < 1e4f && ei < 1e4f) {
+            const int q = ej <= 1.0f ? 1 : f_ceil_i(ej), pp = ei <= 1.0f ? 1 : f_ceil_i(ei);
+            if ((long long)pp * q <= kMaxScatterPhases) { g.P = pp; g.Q = q; }
+        }
+    }
+    return g;
+}
+
+// Index box [i_lo,i_hi] x [j_lo,j_hi] of the crop pixels that can touch frame tile rows [r0,r0+tr) x cols [s0,s0+tw)
+// (unpadded).  Returns false when empty.  A crop pixel touches the tile iff v0 in [r0, r0+tr] and u0 in [s0, s0+tw]
+// (padded tap indices), i.e. v in [r0, r0+tr+1), u in [s0, s0+tw+1).
+STN_HD bool scatter_box(const ScatterGeom &g, int r0, int tr, int s0, int tw, int oH, int oW,
+                        int &i_lo, int &i_hi, int &j_lo, int &j_hi)
+{
+    const float hu = 0.5f * (float)(tw + 1) + g.slack, hv = 0.5f * (float)(tr + 1) + g.slack;
+    const float du = (float)s0 + 0.5f * (float)(tw + 1) - g.cu, dv = (float)r0 + 0.5f * (float)(tr + 1) - g.cv;
+    const float cj = g.i00 * du + g.i01 * dv, ci = g.i10 * du + g.i11 * dv;
+    const float ej = fabsf(g.i00) * hu + fabsf(g.i01) * hv, ei = fabsf(g.i10) * hu + fabsf(g.i11) * hv;
+    const float sj = 0.01f + 2e-6f * (fabsf(cj) + ej), si = 0.01f + 2e-6f * (fabsf(ci) + ei);
+    const float jl = fmaxf(cj - ej - sj, 0.0f), jh = fminf(cj + ej + sj, (float)(oW - 1));
+    const float il = fmaxf(ci - ei - si, 0.0f), ih = fminf(ci + ei + si, (float)(oH - 1));
+    if (!(jl <= jh) || !(il <= ih)) return false;
+    j_lo = f_ceil_i(jl); j_hi = f_floor_i(jh);
+    i_lo = f_ceil_i(il); i_hi = f_floor_i(ih);
+    return j_lo <= j_hi && i_lo <= i_hi;
+}
+
+// cheap conservative test: can crop pixel (i,j) touch the tile at all?
+STN_HD bool scatter_pretest(const ScatterGeom &g, int i, int j, int r0, int tr, int s0, int tw)
+{
+    const float fi = (float)i, fj = (float)j;
+    const float u = g.muj * fj + g.mui * fi + g.cu, v = g.mvj * fj + g.mvi * fi + g.cv;
+    return u >= (float)s0 - g.slack && u <= (float)(s0 + tw + 1) + g.slack &&
+           v >= (float)r0 - g.slack && v <= (float)(r0 + tr + 1) + g.slack;
+}
+
+// The exact part of the scatter: forward chain of crop pixel (xsj, ysi) and which of its four taps land inside
+// the tile rows [r0,r0+tr) x cols [s0,s0+tw) (unpadded) with a non-zero weight.  Zero-weight taps are dropped:
+// they add nothing, and clipped (out-of-image) samples -- which the phase argument does not cover -- only ever
+// have zero-weight or zero-frame taps.
+struct ScatterTaps {
+    Tap t;
+    int row0, col0;          // tile-relative position of tap (v0,u0)
+    bool rv0, rv1, cv0, cv1;
+};
+
+STN_HD bool scatter_taps(const Theta &th, float xsj, float ysi, int H, int W, int r0, int tr, int s0, int tw,
+                         ScatterTaps &o)
+{
+    o.t = make_tap(grid_elem(th.t00, th.t01, th.t02, xsj, ysi), grid_elem(th.t10, th.t11, th.t12, xsj, ysi), H, W);
+    o.row0 = o.t.v0 - 1 - r0;
+    o.col0 = o.t.u0 - 1 - s0;
+    o.rv0 = o.row0 >= 0 && o.row0 < tr && o.t.wv1 != 0.0f;
+    o.rv1 = o.row0 + 1 >= 0 && o.row0 + 1 < tr && o.t.wv0 != 0.0f;
+    o.cv0 = o.col0 >= 0 && o.col0 < tw && o.t.wu1 != 0.0f;
+    o.cv1 = o.col0 + 1 >= 0 && o.col0 + 1 < tw && o.t.wu0 != 0.0f;
+    return (o.rv0 || o.rv1) && (o.cv0 || o.cv1);
+}
+
+// first index >= lo that is congruent to c modulo m
+STN_HD int first_congruent(int lo, int c, int m) { return lo + (((c - lo) % m) + m) % m; }
+
 }  // namespace stn

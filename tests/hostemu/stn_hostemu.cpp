@@ -101,7 +101,96 @@ void emu_crop_bwd(const float *x, const float *theta, float mask01, const float 
     }
 }
 
-// number of (i, j) candidates the scanline enumeration visits for one frame -- efficiency probe for tests
-long long emu_count_candidates(const float *theta, float mask01, int h, int w, int oh, int ow);
+// The tile-scatter formulation of gx exactly as stn_bwd_kernel's gx role runs it (same geometry, box, pre-test,
+// phases and exact tap code from stn_math.cuh), executed serially, with a per-phase write set: returns the number
+// of shared-memory addresses that two crop pixels of the SAME phase wrote -- which on the GPU would be a race.
+// stats[0] = crop pixels fully evaluated, stats[1] = crop pixels pre-tested, stats[2] = crops sent to the gather
+// fallback, stats[3] = largest phase count.
+long long emu_gx_scatter(const float *theta, float mask01, const float *gy, float *gx,
+                         int n, int k, int c, int h, int w, int oh, int ow, int tile_rows, int tile_cols, long long *stats)
+{
+    const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
+    const int npx = oh * ow;
+    const size_t plane = (size_t)h * w;
+    std::vector<float> xs(ow), ys(oh);
+    for (int j = 0; j < ow; ++j) xs[j] = linspace_pm1(j, ow, xstep);
+    for (int i = 0; i < oh; ++i) ys[i] = linspace_pm1(i, oh, ystep);
+    const int frames = n / k;
+    const int twp = (tile_cols + 3) & ~3;
+    long long conflicts = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    std::vector<float> tile((size_t)c * tile_rows * twp);
+    std::vector<int> stamp((size_t)c * tile_rows * twp);
+    std::vector<ScatterGeom> geom(k);
+    std::vector<InvCrop> inv(k);
+    int phase_id = 0;
+    for (int f = 0; f < frames; ++f) {
+        bool any_fb = false;
+        for (int kk = 0; kk < k; ++kk) {
+            const Theta th = load_theta_masked(theta + 6 * (f * k + kk), mask01);
+            geom[kk] = make_scatter_geom(th, h, w, oh, ow);
+            if (geom[kk].P == 0) { inv[kk] = make_inv_crop(th, h, w, oh, ow); any_fb = true; stats[2]++; }
+            else if ((long long)geom[kk].P * geom[kk].Q > stats[3]) stats[3] = (long long)geom[kk].P * geom[kk].Q;
+        }
+        for (int r0 = 0; r0 < h; r0 += tile_rows)
+            for (int s0 = 0; s0 < w; s0 += tile_cols) {
+                const int tr = h - r0 < tile_rows ? h - r0 : tile_rows, tw = w - s0 < tile_cols ? w - s0 : tile_cols;
+                std::fill(tile.begin(), tile.end(), 0.f);
+                std::fill(stamp.begin(), stamp.end(), -1);
+                const int tile_plane = tile_rows * twp;
+                for (int kk = 0; kk < k; ++kk) {
+                    const ScatterGeom &g = geom[kk];
+                    if (g.P == 0) continue;
+                    int i_lo, i_hi, j_lo, j_hi;
+                    if (!scatter_box(g, r0, tr, s0, tw, oh, ow, i_lo, i_hi, j_lo, j_hi)) continue;
+                    const float *gyc = gy + (size_t)(f * k + kk) * c * npx;
+                    for (int cp = 0; cp < g.P; ++cp)
+                        for (int cq = 0; cq < g.Q; ++cq) {
+                            ++phase_id;
+                            for (int i = first_congruent(i_lo, cp, g.P); i <= i_hi; i += g.P)
+                                for (int j = first_congruent(j_lo, cq, g.Q); j <= j_hi; j += g.Q) {
+                                    stats[1]++;
+                                    if (!scatter_pretest(g, i, j, r0, tr, s0, tw)) continue;
+                                    stats[0]++;
+                                    ScatterTaps st;
+                                    if (!scatter_taps(g.th, xs[j], ys[i], h, w, r0, tr, s0, tw, st)) continue;
+                                    for (int ch = 0; ch < c; ++ch) {
+                                        const float gv = gyc[(size_t)ch * npx + (size_t)i * ow + j];
+                                        const float a1 = f_mul(gv, st.t.wu1), a0 = f_mul(gv, st.t.wu0);
+                                        const int base = ch * tile_plane + st.row0 * twp + st.col0;
+                                        const int offs[4] = {0, 1, twp, twp + 1};
+                                        const bool ok[4] = {st.rv0 && st.cv0, st.rv0 && st.cv1, st.rv1 && st.cv0, st.rv1 && st.cv1};
+                                        const float val[4] = {f_mul(a1, st.t.wv1), f_mul(a0, st.t.wv1), f_mul(a1, st.t.wv0), f_mul(a0, st.t.wv0)};
+                                        for (int t4 = 0; t4 < 4; ++t4)
+                                            if (ok[t4]) {
+                                                const int ad = base + offs[t4];
+                                                if (stamp[ad] == phase_id) ++conflicts;
+                                                stamp[ad] = phase_id;
+                                                tile[ad] = f_add(tile[ad], val[t4]);
+                                            }
+                                    }
+                                }
+                        }
+                }
+                // everything the exact taps say touches the tile must have been found by box + pre-test: verified by
+                // comparing the result with the oracle in the test
+                for (int row = 0; row < tr; ++row)
+                    for (int col = 0; col < tw; ++col)
+                        for (int c0 = 0; c0 < c; c0 += 3) {
+                            const int nc = c - c0 < 3 ? c - c0 : 3;
+                            float acc[3] = {0, 0, 0};
+                            for (int ch = 0; ch < nc; ++ch) acc[ch] = tile[(c0 + ch) * tile_plane + row * twp + col];
+                            if (any_fb)
+                                for (int kk = 0; kk < k; ++kk)
+                                    if (geom[kk].P == 0)
+                                        gather_from_crop<3>(inv[kk], xs.data(), ys.data(), h, w, oh, ow, r0 + row + 1, s0 + col + 1,
+                                                            gy + ((size_t)(f * k + kk) * c + c0) * npx, nc, LoadF(), acc);
+                            for (int ch = 0; ch < nc; ++ch)
+                                gx[((size_t)f * c + c0 + ch) * plane + (size_t)(r0 + row) * w + s0 + col] = acc[ch];
+                        }
+            }
+    }
+    return conflicts;
+}
 
 }  // extern "C"

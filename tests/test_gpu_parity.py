@@ -120,12 +120,18 @@ def test_hard_transforms_and_ragged_shapes(G, shape):
     _full_check(G, x, theta, (oh, ow), 1.0, 1, seed=5)
 
 
-def test_identity_reproduces_full_size_frames(G):
-    # size-independent property at BASELINE config 3's frame size
-    x = np.random.default_rng(0).random((4, 3, 512, 512), dtype=np.float32)
-    theta = np.tile(np.array([[1, 0, 0], [0, 1, 0]], np.float32), (4, 1, 1))
-    y, _ = G.crop_fwd(x, theta, (512, 512))
-    assert np.array_equal(y, x)
+def test_identity_at_full_frame_size(G):
+    # BASELINE config 3's frame size, crop as large as the frame: bit-exact vs the oracle, and the frame itself up to
+    # the float32 rounding of linspace (the identity grid does not land exactly on pixel centres at 512 points)
+    x = np.random.default_rng(0).random((2, 3, 512, 512), dtype=np.float32)
+    theta = np.tile(np.array([[1, 0, 0], [0, 1, 0]], np.float32), (2, 1, 1))
+    y, grid = G.crop_fwd(x, theta, (512, 512))
+    y0, grid0 = oc.crop_forward(x, theta, (512, 512))
+    assert np.array_equal(grid, grid0) and np.array_equal(y, y0)
+    assert np.abs(y - x).max() < 1e-4
+    x8 = x[:, :, :9, :17].copy()                       # 9 x 17: every linspace point is exact -> exact copy
+    y8, _ = G.crop_fwd(x8, theta, (9, 17))
+    assert np.array_equal(y8, x8)
 
 
 @pytest.mark.parametrize("name", ["cfg3", "cfg4"])

@@ -31,6 +31,8 @@ def emu():
     lib.emu_crop_fwd.argtypes = [_f, _f, ctypes.c_float, _f, _f] + [ctypes.c_int] * 7
     lib.emu_crop_bwd.argtypes = [_f, _f, ctypes.c_float, _f, _f, _f, _f, _f] + [ctypes.c_int] * 7
     lib.emu_crop_fwd.restype = lib.emu_crop_bwd.restype = None
+    lib.emu_gx_scatter.argtypes = [_f, ctypes.c_float, _f, _f] + [ctypes.c_int] * 9 + [ctypes.POINTER(ctypes.c_longlong)]
+    lib.emu_gx_scatter.restype = ctypes.c_longlong
     return lib
 
 
@@ -52,6 +54,16 @@ def run_emu(lib, x, theta, osz, gy, gg, mask, k):
     return y, grid, gt, gx, ggo
 
 
+def run_scatter(lib, x, theta, osz, gy, mask, k, tile_rows, tile_cols):
+    b, c, h, w = x.shape
+    n = theta.shape[0]
+    oh, ow = osz
+    gx = np.full_like(x, np.nan)
+    stats = (ctypes.c_longlong * 4)()
+    conflicts = lib.emu_gx_scatter(_p(theta), mask, _p(gy), _p(gx), n, k, c, h, w, oh, ow, tile_rows, tile_cols, stats)
+    return gx, conflicts, list(stats)
+
+
 def check(lib, x, theta, osz, mask=1.0, k=1, seed=0):
     rng = np.random.default_rng(seed)
     n, c = theta.shape[0], x.shape[1]
@@ -68,6 +80,14 @@ def check(lib, x, theta, osz, mask=1.0, k=1, seed=0):
     assert np.abs(gx - gx0).max() <= 2e-6 * sc, ("gx", np.abs(gx - gx0).max(), sc)
     sc = max(1.0, float(np.abs(gt0).max()))
     assert np.abs(gt - gt0).max() <= 1e-4 * sc, ("gtheta", np.abs(gt - gt0).max(), sc)
+    # the tile-scatter formulation the GPU actually runs for gx, on two tilings: complete and race free
+    h, w = x.shape[2:]
+    sc = max(1.0, float(np.abs(gx0).max()))
+    for tr, tc in ((5, w), (max(1, h // 2), max(4, (w // 3) & ~3)), (h, w)):
+        gxs, conflicts, stats = run_scatter(lib, x, theta, osz, gy, mask, k, tr, tc)
+        assert conflicts == 0, ("same-phase write conflicts", conflicts, stats)
+        assert not np.isnan(gxs).any()
+        assert np.abs(gxs - gx0).max() <= 2e-6 * sc, ("gx scatter", tr, tc, np.abs(gxs - gx0).max(), sc, stats)
 
 
 @pytest.mark.parametrize("wl,batch,mask", [("cfg2", 3, 1.0), ("cfg1", 2, 0.0), ("cfg3", 1, 0.0), ("cfg4", 1, 0.0)])
