@@ -29,8 +29,8 @@ struct CropParams {
     double xstep, ystep;     // 2/(oW-1), 2/(oH-1)
     int px_per_cta;          // crop pixels handled by one CTA of the per-crop roles
     int ctas_per_crop;       // == cluster size in the backward theta role
-    // backward gx role: CTAs [0, gx_ctas) own one tile of one frame each; the rest reduce gtheta
-    int gx_ctas, gx_tiles_total, gx_tiles_per_frame, gx_tiles_x;
+    // backward gx role: CTAs [0, gx_ctas), eight warp-owned tiles of one frame each; the rest reduce gtheta
+    int gx_ctas, gx_ctas_per_frame, gx_tiles_per_frame, gx_tiles_x;
     int gx_tile_rows, gx_tile_cols, gx_tile_pitch, gx_tile_bytes;
     int gx_vec4;             // 128-bit stores of gx are legal (W % 4 == 0, aligned base)
 };

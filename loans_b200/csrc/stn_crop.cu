@@ -49,7 +49,7 @@ struct PxWalk {
 
 // ------------------------------------------------------------------------------------------ forward
 template <typename YT, int CG, bool FROM_GRID>
-__global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const CropParams p)
+__global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ float smem[];
     float *xs = smem, *ys = smem + p.oW;
@@ -210,94 +210,41 @@ struct GyLoader {
     __device__ __forceinline__ float operator()(const GT *p, size_t i) const { return Elem<GT>::load(p, i); }
 };
 
-// Scalar write-out of a tile, plus -- for crops whose transform is too degenerate for the phased scatter -- their
-// contribution gathered per frame pixel (exact, slow, rare).  Kept out of line so that it does not weigh on the
-// register allocation of the fast path.
+#ifndef STN_BWD_MIN_CTAS
+#define STN_BWD_MIN_CTAS 3
+#endif
+
+// e / d for 0 <= e < 2^20 via one multiply (exact there: |error| <= 1.2e-7 * (e/d) < 0.5/d), integer division beyond
+__device__ __forceinline__ int div_small(int e, int d, float inv_d, bool small)
+{
+    return small ? __float2int_rz(((float)e + 0.5f) * inv_d) : e / d;
+}
+
 template <typename GT, int CG>
-__device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys,
-                                              const ScatterGeom *geom, const InvCrop *inv, const float *tile,
+__device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys, const float *tile,
                                               float *gxb, const GT *gy, int b, int c0, int nc,
-                                              int r0, int tr, int s0, int tw, bool any_fallback)
-{
-    const int twp = p.gx_tile_pitch, tile_plane = p.gx_tile_rows * twp;
-    const int npx = p.oH * p.oW, fpx = p.H * p.W;
-    for (int e = threadIdx.x; e < tr * tw; e += kThreads) {
-        const int row = e / tw, col = e - row * tw;
-        float acc[CG];
-#pragma unroll
-        for (int ch = 0; ch < CG; ++ch) acc[ch] = ch < nc ? tile[ch * tile_plane + row * twp + col] : 0.f;
-        if (any_fallback)
-            for (int kk = 0; kk < p.K; ++kk)
-                if (geom[kk].P == 0)
-                    gather_from_crop<CG>(inv[kk], xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
-                                         gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx, nc, GyLoader<GT>(), acc);
-#pragma unroll
-        for (int ch = 0; ch < CG; ++ch)
-            if (ch < nc) gxb[(size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + col] = acc[ch];
-    }
-}
+                                              int r0, int tr, int s0, int tw, bool any_fallback);
 
-__device__ __noinline__ void fill_inv_crop(InvCrop *dst, Theta th, int H, int W, int oH, int oW)
-{
-    *dst = make_inv_crop(th, H, W, oH, oW);
-}
-
-// one crop pixel of the scatter: exact forward chain, then up to 4 taps x nc channels added into the tile
-template <typename GT, int CG>
-__device__ __forceinline__ void scatter_pixel(const CropParams &p, const Theta &th, float xsj, float ysi,
-                                              const GT *gy_px, int nc, int npx,
-                                              float *tile, int tile_plane, int twp, int r0, int tr, int s0, int tw)
-{
-    ScatterTaps st;
-    if (!scatter_taps(th, xsj, ysi, p.H, p.W, r0, tr, s0, tw, st)) return;
-    const Tap &t = st.t;
-    const int row0 = st.row0, col0 = st.col0;
-    const bool rv0 = st.rv0, rv1 = st.rv1, cv0 = st.cv0, cv1 = st.cv1;
-    float g[CG];
-#pragma unroll
-    for (int ch = 0; ch < CG; ++ch)
-        if (ch < nc) g[ch] = Elem<GT>::load(gy_px, ch * npx);
-    float *t00 = tile + row0 * twp + col0;
-#pragma unroll
-    for (int ch = 0; ch < CG; ++ch)
-        if (ch < nc) {
-            float *tc = t00 + ch * tile_plane;
-            const float a1 = f_mul(g[ch], t.wu1), a0 = f_mul(g[ch], t.wu0);      // gy * wu * wv, reference order
-            if (rv0 && cv0) tc[0] = f_add(tc[0], f_mul(a1, t.wv1));
-            if (rv0 && cv1) tc[1] = f_add(tc[1], f_mul(a0, t.wv1));
-            if (rv1 && cv0) tc[twp] = f_add(tc[twp], f_mul(a1, t.wv0));
-            if (rv1 && cv1) tc[twp + 1] = f_add(tc[twp + 1], f_mul(a0, t.wv0));
-        }
-}
-
+// gx role.  Every WARP owns one tile of frame pixels (gx_tile_rows x gx_tile_cols x CG channels) in shared memory and
+// works through it on its own: zero, phased scatter of the crop pixels that touch it, write-out -- synchronising
+// with __syncwarp() only.  The eight warps of a CTA take eight consecutive tiles of the same frame and share one
+// prologue (axis tables + per-crop geometry) behind the CTA's single barrier.
 template <typename GT, int CG>
 __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm,
-                                        ScatterGeom *geom, InvCrop *inv, float *tile)
+                                        const ScatterGeom *geom, float *tiles)
 {
-    const int tiles_x = p.gx_tiles_x, tiles_per_frame = p.gx_tiles_per_frame;
-    const int b = blockIdx.x / tiles_per_frame;
-    const int tix = blockIdx.x - b * tiles_per_frame;
-    const int ty = tix / tiles_x, tx = tix - ty * tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.gx_ctas_per_frame;
+    const int tix = (blockIdx.x - b * p.gx_ctas_per_frame) * kWarps + warp;
+    if (tix >= p.gx_tiles_per_frame) return;                                   // warp-uniform; no CTA barrier below
+    const int ty = tix / p.gx_tiles_x, tx = tix - ty * p.gx_tiles_x;
     const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
     const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
     const int twp = p.gx_tile_pitch;
     const int tile_plane = p.gx_tile_rows * twp;
+    float *tile = tiles + warp * (CG * tile_plane);
     const int npx = p.oH * p.oW, fpx = p.H * p.W;
     const GT *gy = reinterpret_cast<const GT *>(p.gy);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // per-crop geometry of this frame (float32, conservative) -- and whether any crop needs the gather fallback
-    if (threadIdx.x == 0) sm.flags[0] = 0;
-    __syncthreads();
-    for (int kk = threadIdx.x; kk < p.K; kk += kThreads) {
-        const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
-        geom[kk] = make_scatter_geom(th, p.H, p.W, p.oH, p.oW);
-        if (geom[kk].P == 0) {
-            fill_inv_crop(&inv[kk], th, p.H, p.W, p.oH, p.oW);
-            sm.flags[0] = 1;
-        }
-    }
-    __syncthreads();
     const bool any_fallback = sm.flags[0] != 0;
 
     for (int c0 = 0; c0 < p.C; c0 += CG) {
@@ -305,55 +252,115 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
         {   // zero the tile
             float4 *t4 = reinterpret_cast<float4 *>(tile);
             const int n4 = CG * tile_plane / 4;
-            for (int e = threadIdx.x; e < n4; e += kThreads) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();
+        __syncwarp();
         for (int kk = 0; kk < p.K; ++kk) {
             const ScatterGeom &g = geom[kk];
-            if (g.P == 0) continue;                                            // CTA-uniform
+            if (g.P == 0) continue;                                            // gather fallback crop
             int i_lo, i_hi, j_lo, j_hi;
-            if (!scatter_box(g, r0, tr, s0, tw, p.oH, p.oW, i_lo, i_hi, j_lo, j_hi)) continue;   // CTA-uniform
+            if (!scatter_box(g, r0, tr, s0, tw, p.oH, p.oW, i_lo, i_hi, j_lo, j_hi)) continue;
             const GT *gyc = gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx;
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
             for (int cp = 0; cp < P; ++cp)
                 for (int cq = 0; cq < Q; ++cq) {
-                    // rows i == cp (mod P) are dealt to the warps, columns j == cq (mod Q) to the lanes
+                    // phase (cp, cq): crop pixels with i == cp (mod P), j == cq (mod Q), dealt to the 32 lanes
                     const int ia = first_congruent(i_lo, cp, P), ja = first_congruent(j_lo, cq, Q);
-                    for (int i = ia + warp * P; i <= i_hi; i += kWarps * P) {
-                        const float ysi = ys[i];
-                        for (int j = ja + lane * Q; j <= j_hi; j += 32 * Q) {
-                            if (!scatter_pretest(g, i, j, r0, tr, s0, tw)) continue;
-                            scatter_pixel<GT, CG>(p, th, xs[j], ysi, gyc + i * p.oW + j, nc, npx,
-                                                  tile, tile_plane, twp, r0, tr, s0, tw);
-                        }
+                    const int nrows = ia <= i_hi ? (i_hi - ia) / P + 1 : 0;
+                    const int ncols = ja <= j_hi ? (j_hi - ja) / Q + 1 : 0;
+                    const int total = nrows * ncols;
+                    const bool small = total < (1 << 20);
+                    const float inv_nc = 1.0f / (float)max(ncols, 1);
+                    for (int e = lane; e < total; e += 32) {
+                        const int rr = div_small(e, ncols, inv_nc, small);
+                        const int i = ia + rr * P, j = ja + (e - rr * ncols) * Q;
+                        if (!scatter_pretest(g, i, j, r0, tr, s0, tw)) continue;
+                        float gv[CG];
+                        const GT *gp = gyc + i * p.oW + j;
+#pragma unroll
+                        for (int ch = 0; ch < CG; ++ch) gv[ch] = ch < nc ? Elem<GT>::load(gp, ch * npx) : 0.f;
+                        ScatterTaps st;
+                        if (!scatter_taps(th, xs[j], ys[i], p.H, p.W, r0, tr, s0, tw, st)) continue;
+                        const Tap &t = st.t;
+                        float *t00 = tile + st.row0 * twp + st.col0;
+                        const bool b00 = st.rv0 && st.cv0, b01 = st.rv0 && st.cv1, b10 = st.rv1 && st.cv0, b11 = st.rv1 && st.cv1;
+#pragma unroll
+                        for (int ch = 0; ch < CG; ++ch)
+                            if (ch < nc) {
+                                float *tc = t00 + ch * tile_plane;
+                                const float a1 = f_mul(gv[ch], t.wu1), a0 = f_mul(gv[ch], t.wu0);   // gy * wu * wv, reference order
+                                if (b00) tc[0] = f_add(tc[0], f_mul(a1, t.wv1));
+                                if (b01) tc[1] = f_add(tc[1], f_mul(a0, t.wv1));
+                                if (b10) tc[twp] = f_add(tc[twp], f_mul(a1, t.wv0));
+                                if (b11) tc[twp + 1] = f_add(tc[twp + 1], f_mul(a0, t.wv0));
+                            }
                     }
-                    __syncthreads();                                           // phase (and crop) boundary
+                    __syncwarp();                                              // phase (and crop) boundary
                 }
         }
         // write the tile out: each gx element exactly once, zeros included
         float *gxb = p.gx + ((size_t)b * p.C + c0) * fpx;
         if (p.gx_vec4 && !any_fallback) {
             const int tw4 = tw >> 2;                                           // tw % 4 == 0 guaranteed by the host
-            for (int ch = 0; ch < nc; ++ch)
-                for (int e = threadIdx.x; e < tr * tw4; e += kThreads) {
-                    const int row = e / tw4, c4 = e - row * tw4;
-                    const float4 v = *reinterpret_cast<const float4 *>(tile + ch * tile_plane + row * twp + 4 * c4);
-                    *reinterpret_cast<float4 *>(gxb + (size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + 4 * c4) = v;
-                }
+            const int total = tr * tw4;
+            int row = lane / tw4, c4 = lane - row * tw4;
+            const int drow = 32 / tw4, dc4 = 32 - drow * tw4;
+            for (int e = lane; e < total; e += 32) {
+                const float *tp = tile + row * twp + 4 * c4;
+                float *gp = gxb + (size_t)(r0 + row) * p.W + s0 + 4 * c4;
+                float4 v[CG];
+#pragma unroll
+                for (int ch = 0; ch < CG; ++ch)
+                    if (ch < nc) v[ch] = *reinterpret_cast<const float4 *>(tp + ch * tile_plane);
+#pragma unroll
+                for (int ch = 0; ch < CG; ++ch)
+                    if (ch < nc) *reinterpret_cast<float4 *>(gp + (size_t)ch * fpx) = v[ch];
+                row += drow; c4 += dc4;
+                if (c4 >= tw4) { c4 -= tw4; ++row; }
+            }
         } else {
-            gx_writeout_slow<GT, CG>(p, xs, ys, geom, inv, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
+            gx_writeout_slow<GT, CG>(p, xs, ys, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
         }
-        __syncthreads();
+        __syncwarp();
+    }
+}
+
+// Scalar write-out of a warp's tile, plus -- for crops whose transform is too degenerate for the phased scatter --
+// their contribution gathered per frame pixel (exact, slow, rare).  Out of line: keeps the fast path's registers low.
+template <typename GT, int CG>
+__device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys, const float *tile,
+                                              float *gxb, const GT *gy, int b, int c0, int nc,
+                                              int r0, int tr, int s0, int tw, bool any_fallback)
+{
+    const int lane = threadIdx.x & 31;
+    const int twp = p.gx_tile_pitch, tile_plane = p.gx_tile_rows * twp;
+    const int npx = p.oH * p.oW, fpx = p.H * p.W;
+    for (int e = lane; e < tr * tw; e += 32) {
+        const int row = e / tw, col = e - row * tw;
+        float acc[CG];
+#pragma unroll
+        for (int ch = 0; ch < CG; ++ch) acc[ch] = ch < nc ? tile[ch * tile_plane + row * twp + col] : 0.f;
+        if (any_fallback)
+            for (int kk = 0; kk < p.K; ++kk) {
+                const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
+                if (make_scatter_geom(th, p.H, p.W, p.oH, p.oW).P != 0) continue;
+                const InvCrop inv = make_inv_crop(th, p.H, p.W, p.oH, p.oW);
+                gather_from_crop<CG>(inv, xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
+                                     gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx, nc, GyLoader<GT>(), acc);
+            }
+#pragma unroll
+        for (int ch = 0; ch < CG; ++ch)
+            if (ch < nc) gxb[(size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + col] = acc[ch];
     }
 }
 
 template <typename GT, int CG>
-__global__ void __launch_bounds__(kThreads, 3) stn_bwd_kernel(const CropParams p)
+__global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [tile (gx role only, 16 B aligned)] [BwdSmem] [xs | ys] [ScatterGeom[K]] [InvCrop[K]]
-    float *tile = reinterpret_cast<float *>(smem_raw);
+    // layout: [8 warp tiles (gx role only, 16 B aligned)] [BwdSmem] [xs | ys] [ScatterGeom[K]]
+    float *tiles = reinterpret_cast<float *>(smem_raw);
     unsigned char *q = smem_raw + p.gx_tile_bytes;
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(q);
     q += sizeof(BwdSmem);
@@ -361,11 +368,26 @@ __global__ void __launch_bounds__(kThreads, 3) stn_bwd_kernel(const CropParams p
     float *ys = xs + p.oW;
     q += sizeof(float) * ((p.oW + p.oH + 1) & ~1);
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
-    InvCrop *inv = reinterpret_cast<InvCrop *>(q + sizeof(ScatterGeom) * (p.gx ? p.K : 0));
+    const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
     fill_axis_tables(xs, ys, p.oW, p.oH, p.xstep, p.ystep);
+    if (gx_cta) {
+        // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop
+        const int b = blockIdx.x / p.gx_ctas_per_frame;
+        if (threadIdx.x == 0) sm.flags[0] = 0;
+        if (b < p.N / p.K)
+            for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
+                geom[kk] = make_scatter_geom(load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01),
+                                             p.H, p.W, p.oH, p.oW);
+    }
     __syncthreads();
-    if ((int)blockIdx.x < p.gx_ctas) {
-        if ((int)blockIdx.x < p.gx_tiles_total) gx_role<GT, CG>(p, xs, ys, sm, geom, inv, tile);
+    if (gx_cta) {
+        const int b = blockIdx.x / p.gx_ctas_per_frame;
+        if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
+        // (benign race: every thread that finds a fallback crop writes the same 1)
+        for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
+            if (geom[kk].P == 0) sm.flags[0] = 1;
+        __syncthreads();
+        gx_role<GT, CG>(p, xs, ys, sm, geom, tiles);
     } else {
         theta_role<GT, CG>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
     }
@@ -463,26 +485,28 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     long long gx_ctas = 0;
     size_t smem = sizeof(BwdSmem) + sizeof(float) * (size_t)((p.oW + p.oH + 1) & ~1);
     if (p.gx) {
-        // tile: groups of full rows when they fit the budget, column chunks otherwise; pitch/width multiples of 4
-        const int budget = 40 * 1024 / (int)sizeof(float) / cgsel;               // floats per channel plane
-        int tw = p.W;
-        if ((long long)((p.W + 3) & ~3) * 2 > budget) { tw = (budget / 2) & ~3; if (tw < 4) tw = 4; }
-        const int twp = (tw + 3) & ~3;
-        int tr = budget / twp;
-        if (tr > 32) tr = 32;
+        // one tile per warp: STN_GX_TILE_ROWS rows x (W cut evenly in pieces of <= STN_GX_TILE_COLS, multiple of 4)
+#ifndef STN_GX_TILE_ROWS
+#define STN_GX_TILE_ROWS 8
+#endif
+#ifndef STN_GX_TILE_COLS
+#define STN_GX_TILE_COLS 64
+#endif
+        const int nx = (p.W + STN_GX_TILE_COLS - 1) / STN_GX_TILE_COLS;
+        const int tw = (((p.W + nx - 1) / nx) + 3) & ~3;
+        int tr = STN_GX_TILE_ROWS;
         if (tr > p.H) tr = p.H;
-        if (tr < 1) tr = 1;
-        p.gx_tile_rows = tr; p.gx_tile_cols = tw; p.gx_tile_pitch = twp;
+        p.gx_tile_rows = tr; p.gx_tile_cols = tw; p.gx_tile_pitch = tw;
         p.gx_tiles_x = (p.W + tw - 1) / tw;
         const int tiles_y = (p.H + tr - 1) / tr;
         p.gx_tiles_per_frame = p.gx_tiles_x * tiles_y;
-        p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * twp);
-        p.gx_vec4 = (p.W % 4 == 0 && tw % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
-        const long long tiles = (long long)(p.N / p.K) * p.gx_tiles_per_frame;
-        if (tiles > 0x3fffffffLL) return set_error("crop_bwd: too many gx tiles (%lld)", tiles);
-        p.gx_tiles_total = (int)tiles;
-        gx_ctas = ((tiles + cs - 1) / cs) * cs;                                 // cluster boundaries stay on role boundaries
-        smem += (size_t)p.gx_tile_bytes + (sizeof(ScatterGeom) + sizeof(InvCrop)) * (size_t)p.K;
+        p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps - 1) / kWarps;
+        p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * tw * kWarps);
+        p.gx_vec4 = (p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
+        const long long n_gx = (long long)(p.N / p.K) * p.gx_ctas_per_frame;
+        if (n_gx > 0x3fffffffLL) return set_error("crop_bwd: too many gx CTAs (%lld)", n_gx);
+        gx_ctas = ((n_gx + cs - 1) / cs) * cs;                                  // cluster boundaries stay on role boundaries
+        smem += (size_t)p.gx_tile_bytes + sizeof(ScatterGeom) * (size_t)p.K;
     }
     p.gx_ctas = (int)gx_ctas;
     const long long ctas = theta_ctas + gx_ctas;

@@ -83,7 +83,7 @@ def check(lib, x, theta, osz, mask=1.0, k=1, seed=0):
     # the tile-scatter formulation the GPU actually runs for gx, on two tilings: complete and race free
     h, w = x.shape[2:]
     sc = max(1.0, float(np.abs(gx0).max()))
-    for tr, tc in ((5, w), (max(1, h // 2), max(4, (w // 3) & ~3)), (h, w)):
+    for tr, tc in ((8, min(w, 56)), (max(1, h // 2), max(4, (w // 3) & ~3)), (h, w)):
         gxs, conflicts, stats = run_scatter(lib, x, theta, osz, gy, mask, k, tr, tc)
         assert conflicts == 0, ("same-phase write conflicts", conflicts, stats)
         assert not np.isnan(gxs).any()
