@@ -35,6 +35,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-gx", action="store_true", help="frames do not require grad (what the LoANs step needs)")
+    ap.add_argument("--rotation-ratio", type=float, default=None,
+                    help="override the workload's rotation_dropout ratio (0.0 = as LoANs ships it: axis-aligned crops)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per worker for the cpu_baseline leg")
@@ -222,6 +224,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = W.WORKLOADS[args.workload]
+    if args.rotation_ratio is not None:
+        wl = wl._replace(rotation_ratio=args.rotation_ratio)
     need_gx = not args.no_gx
     steps, warm = args.steps, max(args.warmup, 3)
 

@@ -48,6 +48,11 @@ const char *loans_stn_last_error(void);
 /* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
 unsigned long long loans_stn_launch_count(void);
 
+/* process-wide switches, for tests and A/B measurements.  LOANS_STN_CFG_FORCE_GENERAL != 0: never take the
+ * axis-aligned (mask01 == 0) kernels, always the general-affine ones (results are bit-identical either way). */
+#define LOANS_STN_CFG_FORCE_GENERAL 1
+int loans_stn_configure(int key, int value);
+
 /* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.
  *      Replaces RotationDropout.forward / .backward, reference functions/rotation_droput.py:26-45 / :47-48.
  *      mask01 is drawn ON THE HOST by the caller (train: float(rand(1) < ratio), one draw per call, :41;

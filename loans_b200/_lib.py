@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libloans_stn.so")
 ABI_VERSION = 1
 F32, BF16 = 0, 1
+CFG_FORCE_GENERAL = 1
 
 _lib = None
 
@@ -22,6 +23,7 @@ SIGNATURES = {
     "loans_stn_abi_version": [],
     "loans_stn_last_error": [],
     "loans_stn_launch_count": [],
+    "loans_stn_configure": [_i, _i],
     "loans_stn_rotation_dropout": [_vp, _fl, _vp, _i, _vp],
     "loans_stn_grid_fwd": [_vp, _vp, _i, _i, _i, _vp],
     "loans_stn_grid_bwd": [_vp, _vp, _i, _i, _i, _vp],
@@ -59,6 +61,11 @@ def lib():
 def check(status, what):
     if status != 0:
         raise StnLibraryError("%s failed: %s" % (what, lib().loans_stn_last_error().decode()))
+
+
+def force_general(on):
+    """Tests / A-B runs: never take the axis-aligned kernels (results are bit-identical either way)."""
+    check(lib().loans_stn_configure(CFG_FORCE_GENERAL, int(bool(on))), "loans_stn_configure")
 
 
 def launch_count():

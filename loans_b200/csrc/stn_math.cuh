@@ -411,4 +411,44 @@ STN_HD bool scatter_taps(const Theta &th, float xsj, float ysi, int H, int W, in
 // first index >= lo that is congruent to c modulo m
 STN_HD int first_congruent(int lo, int c, int m) { return lo + (((c - lo) % m) + m) % m; }
 
+// ---------------------------------------------------------------------------------------------------
+// Separable (axis-aligned) transforms: theta01 * mask == theta10 * mask == 0, which is what LoANs always runs
+// (rotation_dropout(..., ratio=0.0), sheep/sheep_localizer.py:61).  Then u depends on j only and v on i only, so
+// the whole coordinate chain is evaluated oW + oH times per crop instead of oH * oW times: one AxisTap per crop
+// column and one per crop row, bit-identical to what make_tap() yields for every pixel of that column / row.
+struct AxisTap {
+    float g;        // grid value (what spatial_transformer_grid outputs for this column / row)
+    float coord;    // unclipped padded coordinate (gradient mask)
+    float w0, w1;   // weight of tap idx0 + 1, weight of tap idx0
+    int idx0;       // first tap, padded index space, in [0, size]
+    float lin;      // the linspace value xs[j] / ys[i] itself (theta-gradient sums)
+};
+
+// t_lin * lin + (t_rot_masked * other) + t_shift with t_rot_masked == +-0: the same operations as grid_elem
+STN_HD AxisTap make_axis_tap(float t_lin, float t_rot_masked, float t_shift, float lin, bool lin_is_x, int size)
+{
+    AxisTap a;
+    a.lin = lin;
+    // grid_elem(t0, t1, t2, xs, ys): row 0 has t0 = t_lin (times xs), t1 = t_rot (times ys);
+    //                                row 1 has t0 = t_rot (times xs), t1 = t_lin (times ys)
+    a.g = lin_is_x ? grid_elem(t_lin, t_rot_masked, t_shift, lin, 0.0f) : grid_elem(t_rot_masked, t_lin, t_shift, 0.0f, lin);
+    a.coord = to_padded_px(a.g, (float)(size - 1));
+    const float c = fminf(fmaxf(a.coord, 0.0f), (float)(size + 1));
+    int i0 = f_floor_i(c);
+    i0 = i0 < 0 ? 0 : (i0 > size ? size : i0);
+    a.idx0 = i0;
+    a.w0 = f_sub(c, (float)i0);
+    a.w1 = f_sub((float)(i0 + 1), c);
+    return a;
+}
+
+STN_HD Tap tap_from_axes(const AxisTap &col, const AxisTap &row)
+{
+    Tap t;
+    t.u = col.coord; t.v = row.coord;
+    t.wu0 = col.w0; t.wu1 = col.w1; t.wv0 = row.w0; t.wv1 = row.w1;
+    t.u0 = col.idx0; t.v0 = row.idx0;
+    return t;
+}
+
 }  // namespace stn

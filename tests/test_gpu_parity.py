@@ -198,3 +198,39 @@ def test_golden_fixture_on_device(G):
         assert np.array_equal(y, g[p + "y"]) and np.array_equal(grid, g[p + "grid"])
         assert np.array_equal(ggo, g[p + "ggrid"])
         assert G.rel_max(gx, g[p + "gx"]) <= 2e-6 and G.rel_max(gt, g[p + "gtheta"]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("name,batch", [("cfg1", None), ("cfg2", 16), ("cfg3", 6), ("cfg4", 3)])
+def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
+    """mask01 == 0 selects the table + TMA-staged kernels; LOANS_STN_CFG_FORCE_GENERAL switches them off."""
+    from loans_b200 import _lib
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True, with_ggrid=True)
+    d["theta"][::5, :, 2] += 0.9                      # some crops hanging out of the frame
+    d["theta"][1::7, 0, 0] *= -1.0                    # mirrored crops
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    try:
+        _lib.force_general(True)
+        y0, g0 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+        b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    finally:
+        _lib.force_general(False)
+    y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+    b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    assert np.array_equal(y0, y1) and np.array_equal(g0, g1)
+    assert np.array_equal(b0[2], b1[2])                                   # ggrid bit-exact
+    assert G.rel_max(b1[1], b0[1]) <= 2e-6 and G.rel_max(b1[0], b0[0]) <= 1e-5
+    yo, go = oc.crop_forward(d["x"], d["theta"], osz, 0.0, k)
+    assert np.array_equal(y1, yo) and np.array_equal(g1, go)
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 24, 7, 9), (1, 8, 8, 16, 16), (2, 12, 20, 1, 5), (4, 16, 12, 6, 1), (3, 64, 2048, 5, 33)])
+def test_axis_aligned_kernels_on_ragged_shapes(G, shape):
+    c, h, w, oh, ow = shape
+    rng = np.random.default_rng(sum(shape))
+    theta = np.array([[[1, 0, 0], [0, 1, 0]], [[-0.8, 0.3, 0.1], [0.2, 0.7, 0]], [[0.05, 0, 0.3], [0, 0.06, -0.2]],
+                      [[0.5, 0, 7.0], [0, 0.5, -9.0]], [[0.9, 0.1, 0.8], [0.05, -0.9, -0.7]], [[0, 0, 0.2], [0, 0, -0.3]],
+                      [[40.0, 3.0, 0.5], [-2.0, 55.0, 0.1]]], np.float32)
+    x = rng.random((len(theta), c, h, w), dtype=np.float32)
+    _full_check(G, x, theta, (oh, ow), 0.0, 1, seed=7)
