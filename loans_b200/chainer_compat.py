@@ -1,0 +1,226 @@
+"""Chainer 4.x binding of libloans_stn.so: the reference-side FFI a LoANs maintainer would add.
+
+    import loans_b200.chainer_compat as stn
+    stn.install()            # once, before sheep/sheep_localizer.py is imported
+
+rebinds ``chainer.functions.spatial_transformer_grid`` / ``spatial_transformer_sampler`` to the FunctionNodes
+below and registers a ``functions.rotation_droput`` module exposing ``rotation_dropout`` / ``RotationDropout``,
+so that reference ``sheep/sheep_localizer.py``, ``sheep/sheep_updater.py`` and ``iou/iou_regressor.py`` run unchanged
+(they reach the three operators only through those names: sheep_localizer.py:2,12,61-63,169-171).
+
+Chainer and cupy are NOT installed in the build container or on the GPU box (chainer==4.1.0 / cupy==4.1.0,
+reference requirements.txt:1-3, are not installable offline), so this module is import-guarded and has only
+been exercised as far as ``tests/test_abi_and_host.py::test_chainer_binding_is_import_guarded`` goes; the same
+C-ABI calls are what the torch front end (loans_b200/functions) makes and what the GPU parity tests check.
+Everything here is pointer plumbing: ``cupy.ndarray.data.ptr`` in, ``cupy.cuda.get_current_stream().ptr`` as the
+stream, outputs allocated from cupy's pool.
+"""
+import sys
+import types
+
+from loans_b200 import _lib
+
+try:                                                     # pragma: no cover - chainer is absent in this environment
+    import chainer
+    from chainer import cuda, function_node
+    from chainer.utils import type_check
+    HAVE_CHAINER = True
+except ImportError:
+    chainer = None
+    HAVE_CHAINER = False
+
+
+def _require():
+    if not HAVE_CHAINER:
+        raise ImportError("loans_b200.chainer_compat needs chainer (4.x) and cupy; use loans_b200.functions with torch "
+                          "tensors otherwise")
+
+
+def _ptr(a):
+    return None if a is None else int(a.data.ptr)
+
+
+def _stream():
+    return int(cuda.cupy.cuda.get_current_stream().ptr)
+
+
+def _gpu_only(*arrays):
+    for a in arrays:
+        if a is not None and not isinstance(a, cuda.ndarray):
+            raise RuntimeError("loans_b200 runs on cupy arrays only (no CPU fallback): move the model with to_gpu()")
+
+
+if HAVE_CHAINER:                                         # pragma: no cover
+
+    class RotationDropout(function_node.FunctionNode):
+        """reference functions/rotation_droput.py:9-48 (old-style Function there; same semantics)."""
+
+        def __init__(self, dropout_ratio):
+            self.dropout_ratio = dropout_ratio
+
+        def check_type_forward(self, in_types):
+            type_check.expect(in_types.size() == 1)
+            x_type = in_types[0]
+            type_check.expect(x_type.dtype.kind == 'f', x_type.ndim == 3, x_type.shape[1] == 2, x_type.shape[2] == 3)
+
+        def forward(self, inputs):
+            x, = inputs
+            _gpu_only(x)
+            xp = cuda.cupy
+            x = xp.ascontiguousarray(x, dtype=xp.float32)
+            if not chainer.config.train:
+                self.mask_value = None
+                value = float(self.dropout_ratio)                      # :33-35
+            else:
+                if not hasattr(self, 'mask_value') or self.mask_value is None:
+                    self.mask_value = float(bool(xp.random.rand(1) < self.dropout_ratio))     # :41, one draw per call
+                value = self.mask_value
+            y = xp.empty_like(x)
+            _lib.check(_lib.lib().loans_stn_rotation_dropout(_ptr(x), value, _ptr(y), x.shape[0], _stream()),
+                       "loans_stn_rotation_dropout")
+            return y,
+
+        def backward(self, indexes, grad_outputs):
+            if self.mask_value is None:
+                raise AttributeError("'RotationDropout' object has no attribute 'mask'")    # :47-48 after a test-mode forward
+            gy = cuda.cupy.ascontiguousarray(grad_outputs[0].data)
+            gx = cuda.cupy.empty_like(gy)
+            _lib.check(_lib.lib().loans_stn_rotation_dropout(_ptr(gy), self.mask_value, _ptr(gx), gy.shape[0], _stream()),
+                       "loans_stn_rotation_dropout")
+            return chainer.Variable(gx),
+
+    def rotation_dropout(x, ratio=.5, **kwargs):
+        return RotationDropout(ratio).apply((x,))[0]
+
+    class SpatialTransformerGrid(function_node.FunctionNode):
+        def __init__(self, output_shape):
+            self.output_shape = tuple(int(v) for v in output_shape)
+
+        def check_type_forward(self, in_types):
+            type_check.expect(in_types.size() == 1)
+            theta_type = in_types[0]
+            type_check.expect(theta_type.dtype.char == 'f', theta_type.ndim == 3, theta_type.shape[1] == 2,
+                              theta_type.shape[2] == 3)
+
+        def forward(self, inputs):
+            theta, = inputs
+            _gpu_only(theta)
+            xp = cuda.cupy
+            theta = xp.ascontiguousarray(theta)
+            oh, ow = self.output_shape
+            grid = xp.empty((theta.shape[0], 2, oh, ow), dtype=xp.float32)
+            _lib.check(_lib.lib().loans_stn_grid_fwd(_ptr(theta), _ptr(grid), theta.shape[0], oh, ow, _stream()),
+                       "loans_stn_grid_fwd")
+            return grid,
+
+        def backward(self, indexes, grad_outputs):
+            xp = cuda.cupy
+            ggrid = xp.ascontiguousarray(grad_outputs[0].data)
+            n, _, oh, ow = ggrid.shape
+            gtheta = xp.empty((n, 2, 3), dtype=xp.float32)
+            _lib.check(_lib.lib().loans_stn_grid_bwd(_ptr(ggrid), _ptr(gtheta), n, oh, ow, _stream()), "loans_stn_grid_bwd")
+            return chainer.Variable(gtheta),
+
+    class FusedSampler(function_node.FunctionNode):
+        """sampler whose grid came straight from our grid node: inputs (x, theta); coordinates are recomputed
+        from theta in registers (loans_stn_crop_fwd / _bwd), the gradient goes to theta directly."""
+
+        def __init__(self, output_shape):
+            self.output_shape = output_shape
+
+        def forward(self, inputs):
+            x, theta = inputs
+            _gpu_only(x, theta)
+            xp = cuda.cupy
+            x, theta = xp.ascontiguousarray(x), xp.ascontiguousarray(theta)
+            self.retain_inputs((0, 1))
+            b, c, h, w = x.shape
+            oh, ow = self.output_shape
+            y = xp.empty((b, c, oh, ow), dtype=xp.float32)
+            _lib.check(_lib.lib().loans_stn_crop_fwd(_ptr(x), _ptr(theta), 1.0, _ptr(y), None, b, 1, c, h, w, oh, ow,
+                                                     _lib.F32, _stream()), "loans_stn_crop_fwd")
+            return y,
+
+        def backward(self, indexes, grad_outputs):
+            xp = cuda.cupy
+            x, theta = (v.data for v in self.get_retained_inputs())
+            gy = xp.ascontiguousarray(grad_outputs[0].data)
+            b, c, h, w = x.shape
+            oh, ow = self.output_shape
+            need_gx = 0 in indexes                      # LoANs passes the frames as a raw array: never needed there
+            gx = xp.empty_like(x) if need_gx else None
+            gtheta = xp.empty_like(theta)
+            _lib.check(_lib.lib().loans_stn_crop_bwd(_ptr(x), _ptr(theta), 1.0, _ptr(gy), None, _ptr(gtheta), _ptr(gx), None,
+                                                     b, 1, c, h, w, oh, ow, _lib.F32, _stream()), "loans_stn_crop_bwd")
+            return (chainer.Variable(gx) if need_gx else None), chainer.Variable(gtheta)
+
+    class SpatialTransformerSampler(function_node.FunctionNode):
+        """explicit-grid sampler (any grid): loans_stn_sampler_fwd / _bwd."""
+
+        def check_type_forward(self, in_types):
+            type_check.expect(2 == in_types.size())
+            x_type, grid_type = in_types
+            type_check.expect(x_type.dtype.char == 'f', grid_type.dtype.char == 'f', x_type.ndim == 4, grid_type.ndim == 4,
+                              grid_type.shape[1] == 2, x_type.shape[0] == grid_type.shape[0])
+
+        def forward(self, inputs):
+            x, grid = inputs
+            _gpu_only(x, grid)
+            xp = cuda.cupy
+            x, grid = xp.ascontiguousarray(x), xp.ascontiguousarray(grid)
+            self.retain_inputs((0, 1))
+            b, c, h, w = x.shape
+            _, _, oh, ow = grid.shape
+            y = xp.empty((b, c, oh, ow), dtype=xp.float32)
+            _lib.check(_lib.lib().loans_stn_sampler_fwd(_ptr(x), _ptr(grid), _ptr(y), b, 1, c, h, w, oh, ow, _lib.F32,
+                                                        _stream()), "loans_stn_sampler_fwd")
+            return y,
+
+        def backward(self, indexes, grad_outputs):
+            xp = cuda.cupy
+            x, grid = (xp.ascontiguousarray(v.data) for v in self.get_retained_inputs())
+            gy = xp.ascontiguousarray(grad_outputs[0].data)
+            b, c, h, w = x.shape
+            _, _, oh, ow = grid.shape
+            gx = xp.empty_like(x) if 0 in indexes else None
+            ggrid = xp.empty_like(grid) if 1 in indexes else None
+            _lib.check(_lib.lib().loans_stn_sampler_bwd(_ptr(x), _ptr(grid), _ptr(gy), _ptr(gx), _ptr(ggrid), b, 1, c, h, w,
+                                                        oh, ow, _lib.F32, _stream()), "loans_stn_sampler_bwd")
+            return (None if gx is None else chainer.Variable(gx)), (None if ggrid is None else chainer.Variable(ggrid))
+
+    def _no_kwargs(kwargs):
+        if 'use_cudnn' in kwargs:
+            raise ValueError("The argument \"use_cudnn\" is not supported anymore. Use "
+                             "chainer.using_config('use_cudnn', value) context where value can be `always`, `never`, or `auto`.")
+        if kwargs:
+            raise TypeError('unexpected keyword arguments: %s' % ', '.join(sorted(kwargs)))
+
+    def spatial_transformer_grid(theta, output_shape, **kwargs):
+        _no_kwargs(kwargs)
+        theta = theta if isinstance(theta, chainer.Variable) else chainer.Variable(theta)
+        grid, = SpatialTransformerGrid(output_shape).apply((theta,))
+        grid._stn_origin = (theta, id(grid.data))               # note for the sampler: which theta this grid came from
+        return grid
+
+    def spatial_transformer_sampler(x, grid, **kwargs):
+        _no_kwargs(kwargs)
+        origin = getattr(grid, '_stn_origin', None)
+        if origin is not None and origin[1] == id(grid.data) and origin[0].shape[0] == grid.shape[0]:
+            return FusedSampler(grid.shape[2:]).apply((x, origin[0]))[0]
+        return SpatialTransformerSampler().apply((x, grid))[0]
+
+
+def install():
+    """Rebind the three operator names the reference uses.  Call before importing sheep.sheep_localizer."""
+    _require()
+    import chainer.functions as F                              # pragma: no cover
+    F.spatial_transformer_grid = spatial_transformer_grid      # pragma: no cover
+    F.spatial_transformer_sampler = spatial_transformer_sampler
+    F.array.spatial_transformer_grid.spatial_transformer_grid = spatial_transformer_grid
+    F.array.spatial_transformer_sampler.spatial_transformer_sampler = spatial_transformer_sampler
+    mod = types.ModuleType("functions.rotation_droput")        # sic: the typo is the reference's import path
+    mod.rotation_dropout = rotation_dropout
+    mod.RotationDropout = RotationDropout
+    pkg = sys.modules.setdefault("functions", types.ModuleType("functions"))
+    pkg.rotation_droput = mod
+    sys.modules["functions.rotation_droput"] = mod

@@ -62,6 +62,22 @@ __device__ __forceinline__ void fill_axis_tables(float *xs, float *ys, int oW, i
     }
 }
 
+__device__ __forceinline__ float lin_x_at(const CropParams &p, int j)
+{
+    return linspace_pm1(j, p.oW, p.xstep);
+}
+__device__ __forceinline__ float lin_y_at(const CropParams &p, int i)
+{
+    return linspace_pm1(i, p.oH, p.ystep);
+}
+__device__ __forceinline__ void fill_axis_tables(const CropParams &p, float *xs, float *ys)
+{
+    for (int k = threadIdx.x; k < p.oW + p.oH; k += blockDim.x) {
+        if (k < p.oW) xs[k] = lin_x_at(p, k);
+        else ys[k - p.oW] = lin_y_at(p, k - p.oW);
+    }
+}
+
 // ---- host-side error plumbing (definitions in stn_abi.cu)
 int set_error(const char *fmt, ...);
 void count_launch(int n = 1);

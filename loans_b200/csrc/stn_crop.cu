@@ -24,37 +24,21 @@
 #include <cooperative_groups.h>
 
 #include "stn_common.cuh"
+#include "stn_theta_role.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace stn {
 
-// per-thread walk over a CTA's share of the crop pixels without divisions in the loop
-struct PxWalk {
-    int q, i, j;
-    int di, dj, ow;
-    __device__ __forceinline__ PxWalk(int q0, int ow_) : q(q0), ow(ow_)
-    {
-        i = q0 / ow_;
-        j = q0 - i * ow_;
-        di = kThreads / ow_;
-        dj = kThreads - di * ow_;
-    }
-    __device__ __forceinline__ void next()
-    {
-        q += kThreads; i += di; j += dj;
-        if (j >= ow) { j -= ow; ++i; }
-    }
-};
-
 // ------------------------------------------------------------------------------------------ forward
-template <typename YT, int CG, bool FROM_GRID>
+template <typename YT, int CG, bool FROM_GRID, bool EXACT>
 __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant__ CropParams p)
 {
+    const int C = EXACT ? CG : p.C;          // EXACT: one channel group covers all channels, loops fold away
     extern __shared__ float smem[];
     float *xs = smem, *ys = smem + p.oW;
     if (!FROM_GRID) {
-        fill_axis_tables(xs, ys, p.oW, p.oH, p.xstep, p.ystep);
+        fill_axis_tables(p, xs, ys);
         __syncthreads();
     }
     const int n = blockIdx.x / p.ctas_per_crop;
@@ -64,8 +48,8 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
     Theta th = {};
     if (!FROM_GRID) th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const int plane = p.H * p.W;
-    const float *xb = p.x + (size_t)(n / p.K) * p.C * plane;
-    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * p.C * npx;
+    const float *xb = p.x + (size_t)(n / p.K) * C * plane;
+    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * C * npx;
     float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
     const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
 
@@ -88,14 +72,14 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
         const Weights4 wt = make_weights(t);
         const float *xc = xb;
         YT *yc = yb + w.q;
-        for (int c0 = 0; c0 < p.C; c0 += CG) {
+        for (int c0 = 0; c0 < C; c0 += CG) {
             float v[CG][4];
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C) load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                if (c0 + ch < C) load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C) Elem<YT>::store(yc, ch * npx, interp(wt, v[ch][0], v[ch][1], v[ch][2], v[ch][3]));
+                if (c0 + ch < C) Elem<YT>::store(yc, ch * npx, interp(wt, v[ch][0], v[ch][1], v[ch][2], v[ch][3]));
             xc += CG * plane;
             yc += CG * npx;
         }
@@ -103,108 +87,6 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ backward
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-struct BwdSmem {
-    float red[kWarps][6];
-    float part[6];        // this CTA's partial gtheta sums, read by cluster rank 0 through DSMEM
-    int flags[2];
-};
-
-template <typename GT, int CG>
-__device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
-{
-    const int cs = p.ctas_per_crop;
-    const int n = cta / cs;
-    const int rank = cta - n * cs;
-    const int npx = p.oH * p.oW;
-    const int q_end = min(npx, (rank + 1) * p.px_per_cta);
-    const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
-    const int plane = p.H * p.W;
-    const float *xb = p.x + (size_t)(n / p.K) * p.C * plane;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * p.C * npx;
-    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
-    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
-
-    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (PxWalk w(rank * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
-        const float xsj = xs[w.j], ysi = ys[w.i];
-        const Tap t = make_tap(grid_elem(th.t00, th.t01, th.t02, xsj, ysi),
-                               grid_elem(th.t10, th.t11, th.t12, xsj, ysi), p.H, p.W);
-        const TapAddr a = make_tap_addr(t, p.H, p.W);
-        float su = 0.f, sv = 0.f;
-        const float *xc = xb;
-        const GT *gc = gyb + w.q;
-        for (int c0 = 0; c0 < p.C; c0 += CG) {
-            float v[CG][4], g[CG];
-#pragma unroll
-            for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C) {
-                    load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-                    g[ch] = Elem<GT>::load(gc, ch * npx);
-                }
-#pragma unroll
-            for (int ch = 0; ch < CG; ++ch)
-                if (c0 + ch < p.C) {
-                    float gu, gv;
-                    grad_uv(t, v[ch][0], v[ch][1], v[ch][2], v[ch][3], gu, gv);
-                    gu = f_mul(gu, g[ch]);
-                    gv = f_mul(gv, g[ch]);
-                    if (c0 + ch == 0) { su = gu; sv = gv; }
-                    else { su = f_add(su, gu); sv = f_add(sv, gv); }          // numpy.sum over the channel axis
-                }
-            xc += CG * plane;
-            gc += CG * npx;
-        }
-        finish_grad_uv(t, p.H, p.W, su, sv);
-        if (ggo) {
-            ggo[w.q] = su;
-            ggo[npx + w.q] = sv;
-        }
-        if (ggu) {
-            su = f_add(su, __ldg(ggu + w.q));
-            sv = f_add(sv, __ldg(ggu + npx + w.q));
-        }
-        s[0] = fmaf(su, xsj, s[0]); s[1] = fmaf(su, ysi, s[1]); s[2] += su;
-        s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const float r = warp_sum(s[k]);
-        if (lane == 0) sm.red[warp][k] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        float tot = 0.f;
-#pragma unroll
-        for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
-        sm.part[threadIdx.x] = tot;
-    }
-    float *out = p.gtheta + 6 * (size_t)n;
-    if (cs > 1) {
-        cg::cluster_group cl = cg::this_cluster();
-        cl.sync();                                         // every CTA's part[] is written and visible
-        if (rank == 0 && threadIdx.x < 6) {
-            float tot = 0.f;
-            for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
-            // backward of the rotation mask: [0,1] and [1,0] are scaled (functions/rotation_droput.py:48)
-            if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-            out[threadIdx.x] = tot;
-        }
-        cl.sync();                                         // peers keep their shared memory until rank 0 has read it
-    } else if (threadIdx.x < 6) {
-        float tot = sm.part[threadIdx.x];
-        if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-        out[threadIdx.x] = tot;
-    }
-}
-
 template <typename GT>
 struct GyLoader {
     __device__ __forceinline__ float operator()(const GT *p, size_t i) const { return Elem<GT>::load(p, i); }
@@ -229,10 +111,11 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 // works through it on its own: zero, phased scatter of the crop pixels that touch it, write-out -- synchronising
 // with __syncwarp() only.  The eight warps of a CTA take eight consecutive tiles of the same frame and share one
 // prologue (axis tables + per-crop geometry) behind the CTA's single barrier.
-template <typename GT, int CG>
+template <typename GT, int CG, bool EXACT>
 __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm,
                                         const ScatterGeom *geom, float *tiles)
 {
+    const int C = EXACT ? CG : p.C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.gx_ctas_per_frame;
     const int tix = (blockIdx.x - b * p.gx_ctas_per_frame) * kWarps + warp;
@@ -247,8 +130,8 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
     const GT *gy = reinterpret_cast<const GT *>(p.gy);
     const bool any_fallback = sm.flags[0] != 0;
 
-    for (int c0 = 0; c0 < p.C; c0 += CG) {
-        const int nc = min(CG, p.C - c0);
+    for (int c0 = 0; c0 < C; c0 += CG) {
+        const int nc = EXACT ? CG : min(CG, C - c0);
         {   // zero the tile
             float4 *t4 = reinterpret_cast<float4 *>(tile);
             const int n4 = CG * tile_plane / 4;
@@ -260,7 +143,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
             if (g.P == 0) continue;                                            // gather fallback crop
             int i_lo, i_hi, j_lo, j_hi;
             if (!scatter_box(g, r0, tr, s0, tw, p.oH, p.oW, i_lo, i_hi, j_lo, j_hi)) continue;
-            const GT *gyc = gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx;
+            const GT *gyc = gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
             for (int cp = 0; cp < P; ++cp)
@@ -300,7 +183,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
                 }
         }
         // write the tile out: each gx element exactly once, zeros included
-        float *gxb = p.gx + ((size_t)b * p.C + c0) * fpx;
+        float *gxb = p.gx + ((size_t)b * C + c0) * fpx;
         if (p.gx_vec4 && !any_fallback) {
             const int tw4 = tw >> 2;                                           // tw % 4 == 0 guaranteed by the host
             const int total = tr * tw4;
@@ -355,7 +238,7 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
     }
 }
 
-template <typename GT, int CG>
+template <typename GT, int CG, bool EXACT>
 __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -369,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     q += sizeof(float) * ((p.oW + p.oH + 1) & ~1);
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
     const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
-    fill_axis_tables(xs, ys, p.oW, p.oH, p.xstep, p.ystep);
+    fill_axis_tables(p, xs, ys);
     if (gx_cta) {
         // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop
         const int b = blockIdx.x / p.gx_ctas_per_frame;
@@ -387,9 +270,9 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
         for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
             if (geom[kk].P == 0) sm.flags[0] = 1;
         __syncthreads();
-        gx_role<GT, CG>(p, xs, ys, sm, geom, tiles);
+        gx_role<GT, CG, EXACT>(p, xs, ys, sm, geom, tiles);
     } else {
-        theta_role<GT, CG>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
+        theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
     }
 }
 
@@ -399,10 +282,17 @@ static int pick_channel_group(int C) { return C == 1 ? 1 : (C % 3 == 0 ? 3 : 4);
 template <typename YT, bool FROM_GRID>
 static cudaError_t launch_fwd_t(const CropParams &p, int cgsel, dim3 grid, size_t smem, cudaStream_t s)
 {
+    const bool exact = p.C == cgsel;
     switch (cgsel) {
-    case 1: stn_fwd_kernel<YT, 1, FROM_GRID><<<grid, kThreads, smem, s>>>(p); break;
-    case 3: stn_fwd_kernel<YT, 3, FROM_GRID><<<grid, kThreads, smem, s>>>(p); break;
-    default: stn_fwd_kernel<YT, 4, FROM_GRID><<<grid, kThreads, smem, s>>>(p); break;
+    case 1: stn_fwd_kernel<YT, 1, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p); break;          // C == 1
+    case 3:
+        if (exact) stn_fwd_kernel<YT, 3, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p);
+        else stn_fwd_kernel<YT, 3, FROM_GRID, false><<<grid, kThreads, smem, s>>>(p);
+        break;
+    default:
+        if (exact) stn_fwd_kernel<YT, 4, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p);
+        else stn_fwd_kernel<YT, 4, FROM_GRID, false><<<grid, kThreads, smem, s>>>(p);
+        break;
     }
     return cudaGetLastError();
 }
@@ -435,13 +325,13 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
     return 0;
 }
 
-template <typename GT, int CG>
+template <typename GT, int CG, bool EXACT>
 static cudaError_t launch_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;                 // per template instance; only ever grows
         if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             granted = smem;
         }
@@ -458,16 +348,17 @@ static cudaError_t launch_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG>, p);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT>, p);
 }
 
 template <typename GT>
 static cudaError_t launch_bwd_t(const CropParams &p, int cgsel, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
+    const bool exact = p.C == cgsel;
     switch (cgsel) {
-    case 1: return launch_bwd_tt<GT, 1>(p, ctas, cs, smem, s);
-    case 3: return launch_bwd_tt<GT, 3>(p, ctas, cs, smem, s);
-    default: return launch_bwd_tt<GT, 4>(p, ctas, cs, smem, s);
+    case 1: return launch_bwd_tt<GT, 1, true>(p, ctas, cs, smem, s);
+    case 3: return exact ? launch_bwd_tt<GT, 3, true>(p, ctas, cs, smem, s) : launch_bwd_tt<GT, 3, false>(p, ctas, cs, smem, s);
+    default: return exact ? launch_bwd_tt<GT, 4, true>(p, ctas, cs, smem, s) : launch_bwd_tt<GT, 4, false>(p, ctas, cs, smem, s);
     }
 }
 

@@ -134,10 +134,17 @@ STN_HD TapAddr make_tap_addr(const Tap &t, int H, int W)
 
 STN_HD void load_taps(const float *plane, const TapAddr &a, int W, float &x1, float &x2, float &x3, float &x4)
 {
-    x1 = (a.r0 && a.c0) ? STN_LDG(plane + a.o00) : 0.0f;
-    x2 = (a.r0 && a.c1) ? STN_LDG(plane + a.o00 + 1) : 0.0f;
-    x3 = (a.r1 && a.c0) ? STN_LDG(plane + a.o00 + W) : 0.0f;
-    x4 = (a.r1 && a.c1) ? STN_LDG(plane + a.o00 + W + 1) : 0.0f;
+    // two address registers (top row, bottom row) shared by the tap pairs; the empty asm keeps the compiler from
+    // re-deriving a 64-bit address under every load's own predicate
+    const float *pt = plane + a.o00;
+    const float *pb = pt + W;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(pt), "+l"(pb));
+#endif
+    x1 = (a.r0 && a.c0) ? STN_LDG(pt) : 0.0f;
+    x2 = (a.r0 && a.c1) ? STN_LDG(pt + 1) : 0.0f;
+    x3 = (a.r1 && a.c0) ? STN_LDG(pb) : 0.0f;
+    x4 = (a.r1 && a.c1) ? STN_LDG(pb + 1) : 0.0f;
 }
 
 struct Weights4 {

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include "stn_common.cuh"
+#include "stn_theta_role.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(kThreads) stn_sep_fwd_kernel(const __grid_cons
         fence_barrier_init();
     }
     for (int k = threadIdx.x; k < p.oW + nrows; k += kThreads) {
-        if (k < p.oW) col[k] = make_axis_tap(th.t00, th.t01, th.t02, linspace_pm1(k, p.oW, p.xstep), true, p.W);
-        else row[k - p.oW] = make_axis_tap(th.t11, th.t10, th.t12, linspace_pm1(ia + k - p.oW, p.oH, p.ystep), false, p.H);
+        if (k < p.oW) col[k] = make_axis_tap(th.t00, th.t01, th.t02, lin_x_at(p, k), true, p.W);
+        else row[k - p.oW] = make_axis_tap(th.t11, th.t10, th.t12, lin_y_at(p, ia + k - p.oW), false, p.H);
     }
     __syncthreads();
     const SepStage st = stage_plan(col, p.oW, p.W);
@@ -223,134 +224,20 @@ int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream)
 #define STN_SEP_BWD_MIN_CTAS 4
 #endif
 
-struct AxisTap16 {          // what the gx scatter needs of an AxisTap, one 128-bit shared-memory load
+struct AxisTap16 {          // what the gx role needs of an AxisTap, one 128-bit shared-memory load
     int idx0;
     float w0, w1;
     int pad_;
 };
 
-__device__ __forceinline__ float warp_sum_sep(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+struct RowMatch {           // crop rows whose tap lands on one frame row: [a0, a0+ca) via tap v0 (weight w1),
+    int a0, ca, b0, cb;     //                                             [b0, b0+cb) via tap v1 (weight w0)
+};
 
-// theta role: a cluster of CTAs per crop, each CTA takes a contiguous band of crop rows, stages the frame rows of
-// `sep_rows` crop rows at a time with TMA and reduces its six partial sums; cluster rank 0 adds the partials.
-template <typename GT, int CG>
-__device__ __forceinline__ void sep_theta_role(const CropParams &p, unsigned char *smem_raw, int cta)
-{
-    SepSmem &sm = *reinterpret_cast<SepSmem *>(smem_raw);
-    AxisTap *col = reinterpret_cast<AxisTap *>(smem_raw + sizeof(SepSmem));
-    AxisTap *row = col + p.oW;
-    float *buf = reinterpret_cast<float *>(smem_raw + p.sep_buf_offset);
-    const int pitch = p.sep_pitch;
-    const int cs = p.ctas_per_crop;
-    const int n = cta / cs, rank = cta - n * cs;
-    const int rows_per_cta = (p.oH + cs - 1) / cs;
-    const int ia = rank * rows_per_cta, ib = min(p.oH, ia + rows_per_cta);
-    const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
-    if (threadIdx.x == 0) {
-        mbar_init(&sm.bar, 1);
-        fence_barrier_init();
-    }
-    for (int k = threadIdx.x; k < p.oW; k += kThreads)
-        col[k] = make_axis_tap(th.t00, th.t01, th.t02, linspace_pm1(k, p.oW, p.xstep), true, p.W);
-    const int npx = p.oH * p.oW;
-    const float *frame = p.x + (size_t)(n / p.K) * p.C * p.H * p.W;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * p.C * npx;
-    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
-    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
-    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    uint32_t parity = 0;
-    for (int i0 = ia; i0 < ib; i0 += p.sep_rows) {
-        const int nrows = min(p.sep_rows, ib - i0);
-        __syncthreads();                                   // previous chunk fully consumed (and col[] written)
-        for (int k = threadIdx.x; k < nrows; k += kThreads)
-            row[k] = make_axis_tap(th.t11, th.t10, th.t12, linspace_pm1(i0 + k, p.oH, p.ystep), false, p.H);
-        __syncthreads();
-        const SepStage st = stage_plan(col, p.oW, p.W);
-        stage_issue(p, frame, row, nrows, st, buf, pitch, &sm.bar);
-        // gy does not depend on the staged rows: the first pixel's loads go out before the wait, every later
-        // pixel's one iteration ahead of its use
-        const int cnt = nrows * p.oW;
-        float gnext[CG];
-#pragma unroll
-        for (int ch = 0; ch < CG; ++ch)
-            gnext[ch] = ((int)threadIdx.x < cnt && ch < p.C) ? Elem<GT>::load(gyb, (size_t)ch * npx + (size_t)i0 * p.oW + threadIdx.x) : 0.f;
-        mbar_wait(&sm.bar, parity);
-        parity ^= 1u;
-        for (int e = threadIdx.x; e < cnt; e += kThreads) {
-            const int r = e / p.oW, j = e - r * p.oW;
-            const int q = i0 * p.oW + e;
-            const AxisTap ct = col[j], rt = row[r];
-            const Tap t = tap_from_axes(ct, rt);
-            float su = 0.f, sv = 0.f;
-            for (int c0 = 0; c0 < p.C; c0 += CG) {
-                float g[CG];
-#pragma unroll
-                for (int ch = 0; ch < CG; ++ch)
-                    g[ch] = c0 == 0 ? gnext[ch] : (c0 + ch < p.C ? Elem<GT>::load(gyb, (size_t)(c0 + ch) * npx + q) : 0.f);
-                if (c0 == 0) {
-                    const int en = e + kThreads;
-#pragma unroll
-                    for (int ch = 0; ch < CG; ++ch)
-                        gnext[ch] = (en < cnt && ch < p.C) ? Elem<GT>::load(gyb, (size_t)ch * npx + (size_t)i0 * p.oW + en) : 0.f;
-                }
-#pragma unroll
-                for (int ch = 0; ch < CG; ++ch)
-                    if (c0 + ch < p.C) {
-                        float x1, x2, x3, x4, gu, gv;
-                        staged_taps(buf, pitch, p.C, r, c0 + ch, ct, rt, st, p.H, p.W, x1, x2, x3, x4);
-                        grad_uv(t, x1, x2, x3, x4, gu, gv);
-                        gu = f_mul(gu, g[ch]);
-                        gv = f_mul(gv, g[ch]);
-                        if (c0 + ch == 0) { su = gu; sv = gv; }
-                        else { su = f_add(su, gu); sv = f_add(sv, gv); }
-                    }
-            }
-            finish_grad_uv(t, p.H, p.W, su, sv);
-            if (ggo) { ggo[q] = su; ggo[npx + q] = sv; }
-            if (ggu) { su = f_add(su, __ldg(ggu + q)); sv = f_add(sv, __ldg(ggu + npx + q)); }
-            const float xsj = ct.lin, ysi = rt.lin;
-            s[0] = fmaf(su, xsj, s[0]); s[1] = fmaf(su, ysi, s[1]); s[2] += su;
-            s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
-        }
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const float r = warp_sum_sep(s[k]);
-        if (lane == 0) sm.red[warp][k] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        float tot = 0.f;
-#pragma unroll
-        for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
-        sm.part[threadIdx.x] = tot;
-    }
-    float *out = p.gtheta + 6 * (size_t)n;
-    if (cs > 1) {
-        cg::cluster_group cl = cg::this_cluster();
-        cl.sync();
-        if (rank == 0 && threadIdx.x < 6) {
-            float tot = 0.f;
-            for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
-            if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-            out[threadIdx.x] = tot;
-        }
-        cl.sync();
-    } else if (threadIdx.x < 6) {
-        float tot = sm.part[threadIdx.x];
-        if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-        out[threadIdx.x] = tot;
-    }
-}
+constexpr int kSepOutPerThread = 4;      // float4 outputs per thread and channel in the gx role
 
-// contiguous index range {k : tab[k].idx0 in [lo, hi]} of a monotone table, found by the whole warp with ballots
-__device__ __forceinline__ bool warp_index_range(const AxisTap16 *tab, int n, int lo, int hi, int &ka, int &kb)
+// contiguous index range {k : tab[k].idx0 in [lo, hi]} of a monotone table, found by one warp with ballots
+__device__ __forceinline__ void warp_index_range(const AxisTap16 *tab, int n, int lo, int hi, int &ka, int &kb)
 {
     const int lane = threadIdx.x & 31;
     ka = n; kb = -1;
@@ -363,164 +250,206 @@ __device__ __forceinline__ bool warp_index_range(const AxisTap16 *tab, int n, in
             kb = max(kb, base + 31 - __clz(m));
         }
     }
-    return ka <= kb;
 }
 
-// gx role: warp-owned tiles as in stn_crop.cu, but which crop pixels touch a tile is read off the per-crop column
-// / row tables (no candidate search, no pre-test) and the taps come from the tables (no coordinate chain).
+// gx role for axis-aligned crops, as two separable passes -- gx = Wv^T (gy Wu):
+//   pass 1  T[i][s] = sum_j gy[i][j] * wu(j -> s)        every crop row that reaches this tile is spread along the
+//                                                        frame columns into a shared-memory row (1-D scatter, in Q
+//                                                        conflict-free phases, see ScatterGeom);
+//   pass 2  gx[r][s] = sum_i wv(i -> r) * T[i][s]        every frame row of the tile is a weighted sum of the (at most
+//                                                        two, when down-sampling) T rows that reach it: float4 row
+//                                                        operations, accumulated in registers over the crops of the
+//                                                        frame and written to gx exactly once, zeros included.
+// Products are formed as (gy * wu) * wv like the reference's scatter_add; no atomics, fixed order, deterministic.
 template <typename GT, int CG>
 __device__ __forceinline__ void sep_gx_role(const CropParams &p, unsigned char *smem_raw)
 {
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    AxisTap16 *tabs = reinterpret_cast<AxisTap16 *>(smem_raw + p.gx_tile_bytes);       // per crop: col[oW] then row[oH]
-    int *pq = reinterpret_cast<int *>(tabs + (size_t)p.K * (p.oW + p.oH));              // per crop: P, Q
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.gx_ctas_per_frame;
-    if (b >= p.N / p.K) return;                                                // padding CTA (cluster rounding)
+    // layout: [BwdSmem][xs|ys (theta role)] | tabs[K][oW+oH] | q[K] | rm[TR] | T[nt_cap][CG][twp]
+    unsigned char *base = smem_raw + p.sep_buf_offset;
+    AxisTap16 *tabs = reinterpret_cast<AxisTap16 *>(base);
     const int per = p.oW + p.oH;
+    int *qtab = reinterpret_cast<int *>(tabs + (size_t)p.K * per);
+    int *range = reinterpret_cast<int *>(qtab + ((p.K + 3) & ~3));        // [ia, ib, ja, jb]
+    float *T = reinterpret_cast<float *>(range + 4);
+    const int b = blockIdx.x / p.gx_tiles_per_frame;
+    if (b >= p.N / p.K) return;                                                // padding CTA (cluster rounding)
+    const int tix = blockIdx.x - b * p.gx_tiles_per_frame;
+    const int ty = tix / p.gx_tiles_x, tx = tix - ty * p.gx_tiles_x;
+    const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
+    const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
+    const int twp = p.gx_tile_pitch;
+    const int npx = p.oH * p.oW, fpx = p.H * p.W;
+    const GT *gy = reinterpret_cast<const GT *>(p.gy);
+
+#ifdef STN_DEBUG_GX_ZERO_ONLY
+    {   // experiment: the gx role only writes zeros (how much of the kernel is the dense write itself?)
+        const int tw4z = (tw + 3) >> 2;
+        for (int c = 0; c < p.C; ++c)
+            for (int e = threadIdx.x; e < tr * tw4z; e += kThreads) {
+                const int rr = e / tw4z, c4 = e - rr * tw4z;
+                *reinterpret_cast<float4 *>(p.gx + ((size_t)b * p.C + c) * fpx + (size_t)(r0 + rr) * p.W + s0 + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        return;
+    }
+#endif
+    // tables of the K crops of this frame
     for (int e = threadIdx.x; e < p.K * per; e += kThreads) {
         const int kk = e / per, k = e - kk * per;
         const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
-        const AxisTap a = k < p.oW ? make_axis_tap(th.t00, th.t01, th.t02, linspace_pm1(k, p.oW, p.xstep), true, p.W)
-                                   : make_axis_tap(th.t11, th.t10, th.t12, linspace_pm1(k - p.oW, p.oH, p.ystep), false, p.H);
+        const AxisTap a = k < p.oW ? make_axis_tap(th.t00, th.t01, th.t02, lin_x_at(p, k), true, p.W)
+                                   : make_axis_tap(th.t11, th.t10, th.t12, lin_y_at(p, k - p.oW), false, p.H);
         AxisTap16 t16; t16.idx0 = a.idx0; t16.w0 = a.w0; t16.w1 = a.w1; t16.pad_ = 0;
         tabs[e] = t16;
     }
     for (int kk = threadIdx.x; kk < p.K; kk += kThreads) {
-        const ScatterGeom g = make_scatter_geom(load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01),
-                                                p.H, p.W, p.oH, p.oW);
-        pq[2 * kk] = g.P; pq[2 * kk + 1] = g.Q;
+        // column phase period: two crop columns can share a frame column only if |du| < 2, i.e. |dj| < 2 / |du/dj|
+        const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
+        const float muj = fabsf(th.t00) * (p.oW > 1 ? 2.0f / (float)(p.oW - 1) : 0.0f) * 0.5f * (float)(p.W - 1);
+        const float ej = muj > 1e-6f ? 2.2f / muj : 3.0e9f;
+        qtab[kk] = ej <= 1.0f ? 1 : (ej < (float)p.oW ? (int)ceilf(ej) : p.oW);
     }
-    __syncthreads();
-    const int twp = p.gx_tile_pitch, tile_plane = p.gx_tile_rows * twp;
-    float *tile = tiles + warp * (CG * tile_plane);
-    const int npx = p.oH * p.oW, fpx = p.H * p.W;
-    const GT *gy = reinterpret_cast<const GT *>(p.gy);
-    const int cta_in_frame = blockIdx.x - b * p.gx_ctas_per_frame;
 
-  // the warp works through gx_tiles_per_warp tiles of this frame, one after the other, on its own
-  for (int tt = 0; tt < p.gx_tiles_per_warp; ++tt) {
-    const int tix = (cta_in_frame * p.gx_tiles_per_warp + tt) * kWarps + warp;
-    if (tix >= p.gx_tiles_per_frame) break;
-    const int ty = tix / p.gx_tiles_x, tx = tix - ty * p.gx_tiles_x;
-    const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
-    const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
+    // this thread's outputs: float4 column groups of tile rows
+    const int tw4 = (tw + 3) >> 2;
+    int o_row[kSepOutPerThread], o_c4[kSepOutPerThread];
+    {
+        int row = threadIdx.x / tw4, c4 = threadIdx.x - row * tw4;
+        const int drow = kThreads / tw4, dc4 = kThreads - drow * tw4;
+#pragma unroll
+        for (int m = 0; m < kSepOutPerThread; ++m) {
+            o_row[m] = row < tr ? row : -1;
+            o_c4[m] = c4;
+            row += drow; c4 += dc4;
+            if (c4 >= tw4) { c4 -= tw4; ++row; }
+        }
+    }
 
     for (int c0 = 0; c0 < p.C; c0 += CG) {
         const int nc = min(CG, p.C - c0);
-        {
-            float4 *t4 = reinterpret_cast<float4 *>(tile);
-            const int n4 = CG * tile_plane / 4;
-            for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
+        float4 acc[kSepOutPerThread][CG];
+#pragma unroll
+        for (int m = 0; m < kSepOutPerThread; ++m)
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) acc[m][ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+
         for (int kk = 0; kk < p.K; ++kk) {
-            const int P = pq[2 * kk], Q = pq[2 * kk + 1];
             const AxisTap16 *col = tabs + (size_t)kk * per, *row = col + p.oW;
-            int ja, jb, ia, ib;
-            // taps of column j are padded columns idx0, idx0+1 = unpadded idx0-1, idx0: inside [s0, s0+tw) iff idx0 in [s0, s0+tw]
-            if (!warp_index_range(col, p.oW, s0, s0 + tw, ja, jb)) continue;
-            if (!warp_index_range(row, p.oH, r0, r0 + tr, ia, ib)) continue;
+            __syncthreads();                                   // tables ready / previous crop's T and rm consumed
+            // which crop rows / columns reach the tile at all (tables are monotone: contiguous ranges)
+            if (threadIdx.x < 32) {
+                int ka, kb;
+                warp_index_range(row, p.oH, r0, r0 + tr, ka, kb);
+                if (threadIdx.x == 0) { range[0] = ka; range[1] = kb; }
+            } else if (threadIdx.x < 64) {
+                int ka, kb;
+                warp_index_range(col, p.oW, s0, s0 + tw, ka, kb);
+                if (threadIdx.x == 32) { range[2] = ka; range[3] = kb; }
+            }
+            __syncthreads();
+            const int ia = range[0], ib = range[1], ja = range[2], jb = range[3];
+            if (ia > ib || ja > jb) continue;                  // CTA-uniform: this crop does not reach the tile
             const GT *gyc = gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx;
-            // P == 0 (degenerate scale: many crop rows/columns on one frame pixel): every pixel its own phase
-            const int PP = P > 0 ? P : (ib - ia + 1), QQ = P > 0 ? Q : (jb - ja + 1);
-            for (int cp = 0; cp < PP; ++cp)
-                for (int cq = 0; cq < QQ; ++cq) {
-                    const int i1 = first_congruent(ia, cp, PP), j1 = first_congruent(ja, cq, QQ);
-                    const int nrows = i1 <= ib ? (ib - i1) / PP + 1 : 0;
-                    const int ncols = j1 <= jb ? (jb - j1) / QQ + 1 : 0;
-                    const int total = nrows * ncols;
+            const int Q = qtab[kk];
+            for (int i0 = ia; i0 <= ib; i0 += p.sep_rows) {    // T rows in chunks of sep_rows crop rows
+                const int nt = min(p.sep_rows, ib - i0 + 1);
+                if (i0 != ia) __syncthreads();                 // previous chunk consumed
+                {
+                    float4 *t4 = reinterpret_cast<float4 *>(T);
+                    const int n4 = nt * CG * twp / 4;
+                    for (int e = threadIdx.x; e < n4; e += kThreads) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncthreads();
+                // pass 1: spread gy rows along the frame columns
+                for (int cq = 0; cq < Q; ++cq) {
+                    const int j1 = first_congruent(ja, cq, Q);
+                    const int ncols = j1 <= jb ? (jb - j1) / Q + 1 : 0;
+                    const int total = nt * ncols;
                     const float inv_nc = 1.0f / (float)max(ncols, 1);
-                    // candidate e of this lane -> (i, j); gy of the NEXT candidate is requested before the current
-                    // one is added, so the load latency of a batch hides behind the previous batch
-                    int e = lane, ci = 0, cj = 0;
-                    float gnext[CG];
-#pragma unroll
-                    for (int ch = 0; ch < CG; ++ch) gnext[ch] = 0.f;
-                    if (e < total) {
-                        const int rr = __float2int_rz(((float)e + 0.5f) * inv_nc);
-                        ci = i1 + rr * PP; cj = j1 + (e - rr * ncols) * QQ;
-#pragma unroll
-                        for (int ch = 0; ch < CG; ++ch) if (ch < nc) gnext[ch] = Elem<GT>::load(gyc, (size_t)ch * npx + ci * p.oW + cj);
-                    }
-                    for (; e < total; e += 32) {
-                        const int i = ci, j = cj;
-                        float gv[CG];
-#pragma unroll
-                        for (int ch = 0; ch < CG; ++ch) gv[ch] = gnext[ch];
-                        const int en = e + 32;
-                        if (en < total) {
-                            const int rr = __float2int_rz(((float)en + 0.5f) * inv_nc);
-                            ci = i1 + rr * PP; cj = j1 + (en - rr * ncols) * QQ;
-#pragma unroll
-                            for (int ch = 0; ch < CG; ++ch) if (ch < nc) gnext[ch] = Elem<GT>::load(gyc, (size_t)ch * npx + ci * p.oW + cj);
-                        }
-                        const AxisTap16 ct = col[j], rt = row[i];
-                        const int row0 = rt.idx0 - 1 - r0, col0 = ct.idx0 - 1 - s0;
-                        const bool rv0 = row0 >= 0 && row0 < tr && rt.w1 != 0.0f, rv1 = row0 + 1 >= 0 && row0 + 1 < tr && rt.w0 != 0.0f;
-                        const bool cv0 = col0 >= 0 && col0 < tw && ct.w1 != 0.0f, cv1 = col0 + 1 >= 0 && col0 + 1 < tw && ct.w0 != 0.0f;
-                        const bool b00 = rv0 && cv0, b01 = rv0 && cv1, b10 = rv1 && cv0, b11 = rv1 && cv1;
-                        float *t00 = tile + row0 * twp + col0;
+                    for (int e = threadIdx.x; e < total; e += kThreads) {
+                        const int ii = total < (1 << 20) ? __float2int_rz(((float)e + 0.5f) * inv_nc) : e / ncols;
+                        const int j = j1 + (e - ii * ncols) * Q;
+                        const AxisTap16 ct = col[j];
+                        const GT *gp = gyc + (i0 + ii) * p.oW + j;
+                        const int cc = ct.idx0 - 1 - s0;
+                        const bool v0 = cc >= 0 && cc < tw && ct.w1 != 0.0f, v1 = cc + 1 >= 0 && cc + 1 < tw && ct.w0 != 0.0f;
+                        float *tc = T + (size_t)ii * CG * twp + cc;
 #pragma unroll
                         for (int ch = 0; ch < CG; ++ch)
                             if (ch < nc) {
-                                float *tc = t00 + ch * tile_plane;
-                                const float a1 = f_mul(gv[ch], ct.w1), a0 = f_mul(gv[ch], ct.w0);   // gy * wu * wv
-                                if (b00) tc[0] = f_add(tc[0], f_mul(a1, rt.w1));
-                                if (b01) tc[1] = f_add(tc[1], f_mul(a0, rt.w1));
-                                if (b10) tc[twp] = f_add(tc[twp], f_mul(a1, rt.w0));
-                                if (b11) tc[twp + 1] = f_add(tc[twp + 1], f_mul(a0, rt.w0));
+                                const float g = Elem<GT>::load(gp, (size_t)ch * npx);
+                                if (v0) tc[ch * twp] = f_add(tc[ch * twp], f_mul(g, ct.w1));
+                                if (v1) tc[ch * twp + 1] = f_add(tc[ch * twp + 1], f_mul(g, ct.w0));
                             }
                     }
-                    __syncwarp();
+                    __syncthreads();
+                }
+                // pass 2: weighted sums of T rows into this thread's output registers.  Crop row i reaches padded
+                // frame rows idx0 (weight w1) and idx0 + 1 (weight w0).
+                for (int ii = 0; ii < nt; ++ii) {
+                    const AxisTap16 rt = row[i0 + ii];
+                    const int ta = rt.idx0 - 1 - r0;               // tile row of tap v0; tap v1 is ta + 1
+                    const float *trow = T + (size_t)ii * CG * twp;
+#pragma unroll
+                    for (int m = 0; m < kSepOutPerThread; ++m) {
+                        const float wv = o_row[m] == ta ? rt.w1 : rt.w0;
+                        if ((o_row[m] == ta || o_row[m] == ta + 1) && o_row[m] >= 0) {
+                            const float *tp = trow + 4 * o_c4[m];
+#pragma unroll
+                            for (int ch = 0; ch < CG; ++ch)
+                                if (ch < nc) {
+                                    const float4 t = *reinterpret_cast<const float4 *>(tp + ch * twp);
+                                    acc[m][ch].x = f_add(acc[m][ch].x, f_mul(t.x, wv)); acc[m][ch].y = f_add(acc[m][ch].y, f_mul(t.y, wv));
+                                    acc[m][ch].z = f_add(acc[m][ch].z, f_mul(t.z, wv)); acc[m][ch].w = f_add(acc[m][ch].w, f_mul(t.w, wv));
+                                }
+                        }
+                    }
+                }
+            }
+        }
+        // every gx element of the tile exactly once
+        float *gxb = p.gx + ((size_t)b * p.C + c0) * fpx;
+#pragma unroll
+        for (int m = 0; m < kSepOutPerThread; ++m) {
+            if (o_row[m] < 0) continue;
+            float *gp = gxb + (size_t)(r0 + o_row[m]) * p.W + s0 + 4 * o_c4[m];
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch)
+                if (ch < nc) {
+                    if (p.gx_vec4) {
+                        *reinterpret_cast<float4 *>(gp + (size_t)ch * fpx) = acc[m][ch];
+                    } else {
+                        const float v[4] = {acc[m][ch].x, acc[m][ch].y, acc[m][ch].z, acc[m][ch].w};
+                        for (int k = 0; k < 4; ++k)
+                            if (4 * o_c4[m] + k < tw) gp[(size_t)ch * fpx + k] = v[k];
+                    }
                 }
         }
-        float *gxb = p.gx + ((size_t)b * p.C + c0) * fpx;
-        if (p.gx_vec4) {
-            const int tw4 = tw >> 2;
-            const int total = tr * tw4;
-            int row = lane / tw4, c4 = lane - row * tw4;
-            const int drow = 32 / tw4, dc4 = 32 - drow * tw4;
-            for (int e = lane; e < total; e += 32) {
-                const float *tp = tile + row * twp + 4 * c4;
-                float *gp = gxb + (size_t)(r0 + row) * p.W + s0 + 4 * c4;
-                float4 v[CG];
-#pragma unroll
-                for (int ch = 0; ch < CG; ++ch)
-                    if (ch < nc) v[ch] = *reinterpret_cast<const float4 *>(tp + ch * tile_plane);
-#pragma unroll
-                for (int ch = 0; ch < CG; ++ch)
-                    if (ch < nc) *reinterpret_cast<float4 *>(gp + (size_t)ch * fpx) = v[ch];
-                row += drow; c4 += dc4;
-                if (c4 >= tw4) { c4 -= tw4; ++row; }
-            }
-        } else {
-            for (int e = lane; e < tr * tw; e += 32) {
-                const int row = e / tw, cc = e - row * tw;
-                for (int ch = 0; ch < nc; ++ch)
-                    gxb[(size_t)ch * fpx + (size_t)(r0 + row) * p.W + s0 + cc] = tile[ch * tile_plane + row * twp + cc];
-            }
-        }
-        __syncwarp();
     }
-  }
 }
 
-template <typename GT, int CG>
+template <typename GT, int CG, bool EXACT>
 __global__ void __launch_bounds__(kThreads, STN_SEP_BWD_MIN_CTAS) stn_sep_bwd_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if ((int)blockIdx.x < p.gx_ctas) sep_gx_role<GT, CG>(p, smem_raw);
-    else sep_theta_role<GT, CG>(p, smem_raw, (int)blockIdx.x - p.gx_ctas);
+    if ((int)blockIdx.x < p.gx_ctas) {
+        sep_gx_role<GT, CG>(p, smem_raw);
+    } else {
+        BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
+        float *xs = reinterpret_cast<float *>(smem_raw + sizeof(BwdSmem));
+        float *ys = xs + p.oW;
+        fill_axis_tables(p, xs, ys);
+        __syncthreads();
+        theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
+    }
 }
 
-template <typename GT, int CG>
+template <typename GT, int CG, bool EXACT>
 static cudaError_t launch_sep_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;
         if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_sep_bwd_kernel<GT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(stn_sep_bwd_kernel<GT, CG, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             granted = smem;
         }
@@ -537,81 +466,69 @@ static cudaError_t launch_sep_bwd_tt(const CropParams &p, unsigned ctas, unsigne
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, stn_sep_bwd_kernel<GT, CG>, p);
+    return cudaLaunchKernelEx(&cfg, stn_sep_bwd_kernel<GT, CG, EXACT>, p);
+}
+
+template <typename GT>
+static cudaError_t launch_sep_bwd_t(const CropParams &p, int cgsel, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+{
+    const bool exact = p.C == cgsel;
+    switch (cgsel) {
+    case 1: return launch_sep_bwd_tt<GT, 1, true>(p, ctas, cs, smem, s);
+    case 3: return exact ? launch_sep_bwd_tt<GT, 3, true>(p, ctas, cs, smem, s) : launch_sep_bwd_tt<GT, 3, false>(p, ctas, cs, smem, s);
+    default: return exact ? launch_sep_bwd_tt<GT, 4, true>(p, ctas, cs, smem, s) : launch_sep_bwd_tt<GT, 4, false>(p, ctas, cs, smem, s);
+    }
 }
 
 int launch_sep_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
 {
     if (p.N == 0) return 0;
     const int cgsel = p.C == 1 ? 1 : (p.C % 3 == 0 ? 3 : 4);
-    // theta role: cluster of cs CTAs per crop (rows split evenly), staging sep_rows crop rows at a time
-    const int pitch = (p.W + 3) & ~3;
-    const size_t per_row = (size_t)2 * p.C * pitch * sizeof(float);
-    int rows = (int)((44 * 1024) / per_row);
-    if (rows < 1) return -1;
-    if (rows > 16) rows = 16;
-#ifndef STN_SEP_THETA_CS_MAX
-#define STN_SEP_THETA_CS_MAX 8
-#endif
+    const long long npx = (long long)p.oH * p.oW;
+    // theta role exactly as in the general backward (stn_crop.cu: launch_crop_bwd)
     unsigned cs = 1;
-    while (cs < STN_SEP_THETA_CS_MAX && (long long)p.N * cs < 2LL * kNumSMs && (p.oH + 2 * cs - 1) / (2 * cs) >= 2) cs *= 2;
-    const int rows_per_cta = (p.oH + (int)cs - 1) / (int)cs;
-    if (rows > rows_per_cta) rows = rows_per_cta;
-    p.sep_rows = rows;
-    p.sep_pitch = pitch;
+    while (cs < 8 && (long long)p.N * cs < 2LL * kNumSMs && npx / (2 * cs) >= kThreads / 2) cs *= 2;
     p.ctas_per_crop = (int)cs;
-    size_t off = sizeof(SepSmem) + sizeof(AxisTap) * (size_t)(p.oW + rows);
-    off = (off + 127) & ~(size_t)127;
-    p.sep_buf_offset = (int)off;
-    size_t smem = off + per_row * rows;
+    p.px_per_cta = (int)((npx + cs - 1) / cs);
     const long long theta_ctas = (long long)p.N * cs;
+    size_t smem = sizeof(BwdSmem) + sizeof(float) * (size_t)((p.oW + p.oH + 1) & ~1);
+    smem = (smem + 127) & ~(size_t)127;
+    p.sep_buf_offset = (int)smem;
     long long gx_ctas = 0;
     if (p.gx) {
-#ifndef STN_GX_TILE_ROWS
-#define STN_GX_TILE_ROWS 8
-#endif
-#ifndef STN_GX_TILE_COLS
-#define STN_GX_TILE_COLS 64
-#endif
-        const int nx = (p.W + STN_GX_TILE_COLS - 1) / STN_GX_TILE_COLS;
+        // tile: W cut evenly in column pieces of <= 256 (multiples of 4), rows so that a thread owns <= 4 float4 outputs
+        const int nx = (p.W + 255) / 256;
         const int tw = (((p.W + nx - 1) / nx) + 3) & ~3;
-        int tr = STN_GX_TILE_ROWS;
+        const int tw4 = tw / 4;
+        int tr = (kSepOutPerThread * kThreads) / tw4;
+        if (tr > 16) tr = 16;
         if (tr > p.H) tr = p.H;
+        if (tr < 1) return -1;
         p.gx_tile_rows = tr; p.gx_tile_cols = tw; p.gx_tile_pitch = tw;
         p.gx_tiles_x = (p.W + tw - 1) / tw;
         p.gx_tiles_per_frame = p.gx_tiles_x * ((p.H + tr - 1) / tr);
-        // tiles per warp: the fewest that keep gx CTAs + theta CTAs within about one wave of resident CTAs
-#ifndef STN_SEP_WAVE_CTAS
-#define STN_SEP_WAVE_CTAS (8 * kNumSMs)
-#endif
-        long long gx_budget = (long long)STN_SEP_WAVE_CTAS - theta_ctas;
-        if (gx_budget < STN_SEP_WAVE_CTAS / 2) gx_budget = STN_SEP_WAVE_CTAS / 2;
-        int tpw = 1;
-        while (tpw < 64 && (long long)(p.N / p.K) * ((p.gx_tiles_per_frame + kWarps * tpw - 1) / (kWarps * tpw)) > gx_budget) ++tpw;
-        p.gx_tiles_per_warp = tpw;
-        p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps * tpw - 1) / (kWarps * tpw);
-        p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * tw * kWarps);
         p.gx_vec4 = (p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
-        const size_t gx_smem = (size_t)p.gx_tile_bytes + (sizeof(AxisTap16) * (size_t)(p.oW + p.oH) + 2 * sizeof(int)) * (size_t)p.K;
+        // T rows per chunk: the crop rows that reach a tile when down-sampling by >= 2 (tr / 2 + 2), more if memory allows
+        int nt = tr / 2 + 2;
+        const size_t row_bytes = sizeof(float) * (size_t)cgsel * tw;
+        while (nt < 16 && (size_t)(nt + 1) * row_bytes <= 32 * 1024) ++nt;
+        if ((size_t)nt * row_bytes > 96 * 1024) return -1;
+        p.sep_rows = nt;
+        const size_t tabs = sizeof(AxisTap16) * (size_t)p.K * (p.oW + p.oH) + sizeof(int) * (size_t)((p.K + 3) & ~3)
+                          + 4 * sizeof(int);
+        const size_t gx_smem = (size_t)p.sep_buf_offset + ((tabs + 15) & ~(size_t)15) + (size_t)nt * row_bytes;
         if (gx_smem > 160 * 1024) return -1;                    // too many crops per frame for the tables: general kernel
         if (gx_smem > smem) smem = gx_smem;
-        const long long n_gx = (long long)(p.N / p.K) * p.gx_ctas_per_frame;
+        p.gx_tile_bytes = 0;
+        const long long n_gx = (long long)(p.N / p.K) * p.gx_tiles_per_frame;
         if (n_gx > 0x3fffffffLL) return set_error("sep_bwd: too many gx CTAs (%lld)", n_gx);
         gx_ctas = ((n_gx + cs - 1) / cs) * cs;
     }
     p.gx_ctas = (int)gx_ctas;
     const long long ctas = theta_ctas + gx_ctas;
     if (ctas > 0x7fffffffLL) return set_error("sep_bwd: too many CTAs (%lld)", ctas);
-    cudaError_t e;
-    if (gy_dtype == 0) {
-        e = cgsel == 1 ? launch_sep_bwd_tt<float, 1>(p, (unsigned)ctas, cs, smem, stream)
-          : cgsel == 3 ? launch_sep_bwd_tt<float, 3>(p, (unsigned)ctas, cs, smem, stream)
-                       : launch_sep_bwd_tt<float, 4>(p, (unsigned)ctas, cs, smem, stream);
-    } else {
-        e = cgsel == 1 ? launch_sep_bwd_tt<__nv_bfloat16, 1>(p, (unsigned)ctas, cs, smem, stream)
-          : cgsel == 3 ? launch_sep_bwd_tt<__nv_bfloat16, 3>(p, (unsigned)ctas, cs, smem, stream)
-                       : launch_sep_bwd_tt<__nv_bfloat16, 4>(p, (unsigned)ctas, cs, smem, stream);
-    }
+    cudaError_t e = gy_dtype == 0 ? launch_sep_bwd_t<float>(p, cgsel, (unsigned)ctas, cs, smem, stream)
+                                  : launch_sep_bwd_t<__nv_bfloat16>(p, cgsel, (unsigned)ctas, cs, smem, stream);
     count_launch();
     if (e != cudaSuccess) return set_error("sep_bwd launch failed: %s", cudaGetErrorString(e));
     return 0;

@@ -1,0 +1,135 @@
+// stn_theta_role.cuh -- the theta-gradient role of the backward kernels (shared by the general and the axis-aligned
+// backward): a thread-block CLUSTER per crop; each CTA walks its share of the crop pixels (taps gathered straight
+// from global memory through the read-only path, gy, upstream grid gradient), reduces the six sums of
+// gtheta = ggrid . [xs; ys; 1]^T with warp shuffles and shared memory, and rank 0 of the cluster adds the per-CTA
+// partials through distributed shared memory in a fixed order: deterministic, no atomics, no workspace.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "stn_common.cuh"
+
+namespace stn {
+
+// per-thread walk over a CTA's share of the crop pixels without divisions in the loop
+struct PxWalk {
+    int q, i, j;
+    int di, dj, ow;
+    __device__ __forceinline__ PxWalk(int q0, int ow_) : q(q0), ow(ow_)
+    {
+        i = q0 / ow_;
+        j = q0 - i * ow_;
+        di = kThreads / ow_;
+        dj = kThreads - di * ow_;
+    }
+    __device__ __forceinline__ void next()
+    {
+        q += kThreads; i += di; j += dj;
+        if (j >= ow) { j -= ow; ++i; }
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct BwdSmem {
+    float red[kWarps][6];
+    float part[6];        // this CTA's partial gtheta sums, read by cluster rank 0 through DSMEM
+    int flags[2];
+};
+
+template <typename GT, int CG, bool EXACT>
+__device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
+{
+    const int C = EXACT ? CG : p.C;
+    const int cs = p.ctas_per_crop;
+    const int n = cta / cs;
+    const int rank = cta - n * cs;
+    const int npx = p.oH * p.oW;
+    const int q_end = min(npx, (rank + 1) * p.px_per_cta);
+    const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
+    const int plane = p.H * p.W;
+    const float *xb = p.x + (size_t)(n / p.K) * C * plane;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * C * npx;
+    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
+    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
+
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (PxWalk w(rank * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
+        const float xsj = xs[w.j], ysi = ys[w.i];
+        const Tap t = make_tap(grid_elem(th.t00, th.t01, th.t02, xsj, ysi),
+                               grid_elem(th.t10, th.t11, th.t12, xsj, ysi), p.H, p.W);
+        const TapAddr a = make_tap_addr(t, p.H, p.W);
+        float su = 0.f, sv = 0.f;
+        const float *xc = xb;
+        const GT *gc = gyb + w.q;
+        for (int c0 = 0; c0 < C; c0 += CG) {
+            float v[CG][4], g[CG];
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch)
+                if (c0 + ch < C) {
+                    load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                    g[ch] = Elem<GT>::load(gc, ch * npx);
+                }
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch)
+                if (c0 + ch < C) {
+                    float gu, gv;
+                    grad_uv(t, v[ch][0], v[ch][1], v[ch][2], v[ch][3], gu, gv);
+                    gu = f_mul(gu, g[ch]);
+                    gv = f_mul(gv, g[ch]);
+                    if (c0 + ch == 0) { su = gu; sv = gv; }
+                    else { su = f_add(su, gu); sv = f_add(sv, gv); }          // numpy.sum over the channel axis
+                }
+            xc += CG * plane;
+            gc += CG * npx;
+        }
+        finish_grad_uv(t, p.H, p.W, su, sv);
+        if (ggo) {
+            ggo[w.q] = su;
+            ggo[npx + w.q] = sv;
+        }
+        if (ggu) {
+            su = f_add(su, __ldg(ggu + w.q));
+            sv = f_add(sv, __ldg(ggu + npx + w.q));
+        }
+        s[0] = fmaf(su, xsj, s[0]); s[1] = fmaf(su, ysi, s[1]); s[2] += su;
+        s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float r = warp_sum(s[k]);
+        if (lane == 0) sm.red[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float tot = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
+        sm.part[threadIdx.x] = tot;
+    }
+    float *out = p.gtheta + 6 * (size_t)n;
+    if (cs > 1) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        cl.sync();                                         // every CTA's part[] is written and visible
+        if (rank == 0 && threadIdx.x < 6) {
+            float tot = 0.f;
+            for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
+            // backward of the rotation mask: [0,1] and [1,0] are scaled (functions/rotation_droput.py:48)
+            if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
+            out[threadIdx.x] = tot;
+        }
+        cl.sync();                                         // peers keep their shared memory until rank 0 has read it
+    } else if (threadIdx.x < 6) {
+        float tot = sm.part[threadIdx.x];
+        if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
+        out[threadIdx.x] = tot;
+    }
+}
+
+
+}  // namespace stn

@@ -115,3 +115,16 @@ def test_workload_generator_is_seeded_and_shaped():
     assert np.all(a["theta"][:, 0, 1] == 0)                  # rotation_ratio 0.0 workloads are generated axis-aligned
     c = W.make_inputs(W.WORKLOADS["cfg2"], batch=4)
     assert np.any(c["theta"][:, 0, 1] != 0)                  # cfg2 has no dropout node: general affine
+
+
+def test_chainer_binding_is_import_guarded():
+    # chainer/cupy are absent here: the binding must import cleanly and say so when asked to install
+    from loans_b200 import chainer_compat
+    if chainer_compat.HAVE_CHAINER:
+        pytest.skip("chainer present")
+    with pytest.raises(ImportError):
+        chainer_compat.install()
+    src = open(chainer_compat.__file__).read()
+    for name in ("loans_stn_rotation_dropout", "loans_stn_grid_fwd", "loans_stn_grid_bwd", "loans_stn_sampler_fwd",
+                 "loans_stn_sampler_bwd", "loans_stn_crop_fwd", "loans_stn_crop_bwd"):
+        assert name in src and name in _lib.SIGNATURES
