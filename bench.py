@@ -5,8 +5,10 @@
     python bench.py --impl reference ...                     (the reference's numpy CPU path, restated, on the host cores)
 
 A step = one forward + one backward of the fused path over one batch of synthetic frames of BASELINE.json's
-configs[1] (cfg2: batch 64, 3x224x224 -> 64x64, fp32, general affine theta, gx produced), per GPU (weak
-scaling: the path shards by batch with no collective).  `value` is timed on the device with inputs resident in
+configs[1] (cfg2: batch 64, 3x224x224 -> 64x64, fp32, gx produced), per GPU (weak scaling: the path shards by
+batch with no collective).  The headline runs the path as LoANs ships it -- rotation_dropout(ratio=0.0) in front of
+the grid, i.e. axis-aligned crops (reference sheep/sheep_localizer.py:61); the same steps with a general affine
+theta (no dropout node) are timed in the same run and reported under "variants".  `value` is timed on the device with inputs resident in
 HBM, the steps replayed from CUDA graphs (2 kernel launches per step); `e2e` is the same work through the public
 operators with pinned HOST buffers, copies inside the timed region.  Nothing here reads /root/reference.
 """
@@ -35,8 +37,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-gx", action="store_true", help="frames do not require grad (what the LoANs step needs)")
-    ap.add_argument("--rotation-ratio", type=float, default=None,
-                    help="override the workload's rotation_dropout ratio (0.0 = as LoANs ships it: axis-aligned crops)")
+    ap.add_argument("--rotation-ratio", default="shipped",
+                    help="'shipped' (default): rotation_dropout(ratio=0.0) in front of the grid, as LoANs always calls it "
+                         "(sheep/sheep_localizer.py:61) -> axis-aligned crops; 'none': no dropout node, general affine theta; "
+                         "or a number used as the test-mode mask value")
+    ap.add_argument("--no-variants", action="store_true", help="skip the second (general-affine / as-shipped) timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per worker for the cpu_baseline leg")
@@ -224,8 +229,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = W.WORKLOADS[args.workload]
-    if args.rotation_ratio is not None:
-        wl = wl._replace(rotation_ratio=args.rotation_ratio)
+    rr = args.rotation_ratio
+    wl = wl._replace(rotation_ratio=0.0 if rr == "shipped" else (None if rr == "none" else float(rr)))
     need_gx = not args.no_gx
     steps, warm = args.steps, max(args.warmup, 3)
 
@@ -270,11 +275,11 @@ def run_ours(args):
         return None if t is None else t.data_ptr()
 
     def fwd(e):
-        _lib.check(L.loans_stn_crop_fwd(p(e["x"]), p(e["theta"]), mask01, p(e["y"]), p(e["grid"]), N, K, C, H, Wd, oH, oW,
+        _lib.check(L.loans_stn_crop_fwd(p(e["x"]), p(e["theta"]), float(mask01), p(e["y"]), p(e["grid"]), N, K, C, H, Wd, oH, oW,
                                         dt_code, torch.cuda.current_stream().cuda_stream), "crop_fwd")
 
     def bwd(e):
-        _lib.check(L.loans_stn_crop_bwd(p(e["x"]), p(e["theta"]), mask01, p(e["gy"]), None, p(e["gtheta"]), p(e["gx"]), None,
+        _lib.check(L.loans_stn_crop_bwd(p(e["x"]), p(e["theta"]), float(mask01), p(e["gy"]), None, p(e["gtheta"]), p(e["gx"]), None,
                                         N, K, C, H, Wd, oH, oW, dt_code, torch.cuda.current_stream().cuda_stream), "crop_bwd")
 
     def capture(fn):
@@ -339,6 +344,27 @@ def run_ours(args):
     reps = max(1, steps // S)
     ms_f = timed(lambda: [g_fwd.replay() for _ in range(reps)]) / (reps * S)
     ms_b = timed(lambda: [g_bwd.replay() for _ in range(reps)]) / (reps * S)
+
+    # ---- the other theta regime, same buffers: general affine (mask 1) if the headline is as-shipped, and vice versa
+    variants = {}
+    if not args.no_variants:
+        main_mask = mask01
+        alt_mask = 1.0 if main_mask == 0.0 else 0.0
+        mask01 = alt_mask
+        a_all = capture(lambda: [(fwd(e), bwd(e)) for e in sets])
+        a_fwd = capture(lambda: [fwd(e) for e in sets])
+        a_bwd = capture(lambda: [bwd(e) for e in sets])
+        mask01 = main_mask
+        for _ in range(3):
+            a_all.replay()
+        reps_a = max(1, steps // S)
+        ms_a = timed(lambda: [a_all.replay() for _ in range(reps_a)]) / (reps_a * S)
+        ms_af = timed(lambda: [a_fwd.replay() for _ in range(reps_a)]) / (reps_a * S)
+        ms_ab = timed(lambda: [a_bwd.replay() for _ in range(reps_a)]) / (reps_a * S)
+        variants["general_affine" if alt_mask == 1.0 else "as_shipped_axis_aligned"] = {
+            "mask01": alt_mask, "value": world * N / (ms_a * 1e-3), "unit": UNIT, "us_per_step": ms_a * 1e3,
+            "fwd_us": ms_af * 1e3, "bwd_us": ms_ab * 1e3,
+            "whole_step_frac": (fwd_bytes + bwd_bytes) / (ms_a * 1e-3) / 1e9}
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -410,7 +436,9 @@ def run_ours(args):
                           % (S, set_bytes / 1e6, S * set_bytes / 1e6),
                     "launch": "CUDA-graph replay of the C-ABI calls loans_stn_crop_fwd + loans_stn_crop_bwd"}),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "variants": variants}
+        for v in variants.values():
+            v["whole_step_frac"] = v["whole_step_frac"] / peak
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
