@@ -42,6 +42,7 @@ def parse_args():
                          "(sheep/sheep_localizer.py:61) -> axis-aligned crops; 'none': no dropout node, general affine theta; "
                          "or a number used as the test-mode mask value")
     ap.add_argument("--no-variants", action="store_true", help="skip the second (general-affine / as-shipped) timing")
+    ap.add_argument("--tma-forward", action="store_true", help="opt into the TMA-staged forward kernel (axis-aligned crops)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per worker for the cpu_baseline leg")
@@ -244,6 +245,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    if args.tma_forward:
+        _lib.tma_forward(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -378,7 +381,7 @@ def run_ours(args):
     ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9
     ach_f = fwd_bytes / (ms_f * 1e-3) / 1e9
     ach_s = (fwd_bytes + bwd_bytes) / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "stn_bwd_kernel (theta-gradient clusters + gx gather, one launch)",
+    roofline = {"bound": "hbm", "kernel": "backward launch (gx role + cluster-reduced theta role): stn_sep_bwd_kernel when mask01 == 0, else stn_bwd_kernel",
                 "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_us": ms_b * 1e3,
                 "fwd_kernel": {"achieved": ach_f, "frac": ach_f / peak, "algorithmic_bytes_per_launch": fwd_bytes,

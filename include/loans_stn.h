@@ -48,9 +48,13 @@ const char *loans_stn_last_error(void);
 /* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
 unsigned long long loans_stn_launch_count(void);
 
-/* process-wide switches, for tests and A/B measurements.  LOANS_STN_CFG_FORCE_GENERAL != 0: never take the
- * axis-aligned (mask01 == 0) kernels, always the general-affine ones (results are bit-identical either way). */
+/* process-wide switches, for tests and A/B measurements (results are bit-identical either way).
+ * LOANS_STN_CFG_TMA_FORWARD != 0: forward of axis-aligned crops (mask01 == 0, w % 4 == 0) through the AxisTap-table +
+ *   TMA-bulk-copy-staged kernel (stn_separable.cu) instead of the direct gather.  Default 0: on B200 the direct gather
+ *   measured faster at every BASELINE size (profiles/README.md).
+ * LOANS_STN_CFG_FORCE_GENERAL != 0: never take the axis-aligned kernel, whatever the other switch says. */
 #define LOANS_STN_CFG_FORCE_GENERAL 1
+#define LOANS_STN_CFG_TMA_FORWARD 2
 int loans_stn_configure(int key, int value);
 
 /* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.

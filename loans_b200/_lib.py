@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libloans_stn.so")
 ABI_VERSION = 1
 F32, BF16 = 0, 1
 CFG_FORCE_GENERAL = 1
+CFG_TMA_FORWARD = 2
 
 _lib = None
 
@@ -66,6 +67,11 @@ def check(status, what):
 def force_general(on):
     """Tests / A-B runs: never take the axis-aligned kernels (results are bit-identical either way)."""
     check(lib().loans_stn_configure(CFG_FORCE_GENERAL, int(bool(on))), "loans_stn_configure")
+
+
+def tma_forward(on):
+    """Opt into the TMA-staged forward kernel for axis-aligned crops (mask01 == 0)."""
+    check(lib().loans_stn_configure(CFG_TMA_FORWARD, int(bool(on))), "loans_stn_configure")
 
 
 def launch_count():

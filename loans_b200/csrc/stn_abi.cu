@@ -37,9 +37,9 @@ int launch_sampler_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stream);
 int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);      // -1: shape not supported, use the general kernel
-int launch_sep_bwd(CropParams p, int gy_dtype, cudaStream_t stream);     // likewise
 
 static std::atomic<int> g_force_general{0};
+static std::atomic<int> g_tma_forward{0};
 
 static int need_device(const char *what)
 {
@@ -98,6 +98,7 @@ unsigned long long loans_stn_launch_count(void) { return g_launches.load(std::me
 int loans_stn_configure(int key, int value)
 {
     if (key == LOANS_STN_CFG_FORCE_GENERAL) { g_force_general.store(value != 0); return 0; }
+    if (key == LOANS_STN_CFG_TMA_FORWARD) { g_tma_forward.store(value != 0); return 0; }
     return set_error("loans_stn_configure: unknown key %d", key);
 }
 
@@ -177,8 +178,10 @@ int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y
     if (need_device(what)) return 1;
     CropParams p = base_params(n, k, c, h, w, oh, ow);
     p.x = x; p.theta = theta; p.mask01 = mask01; p.y = y; p.grid_out = grid;
-    // mask01 == 0 (LoANs' ratio = 0.0): every crop is axis-aligned -> table + TMA-staged kernel
-    if (mask01 == 0.0f && !g_force_general.load() && w % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // mask01 == 0 (LoANs' ratio = 0.0): every crop is axis-aligned -> the table + TMA-staged kernel applies.  It is
+    // opt-in: measured on B200 it is never faster than the direct gather (profiles/README.md), so the default is off.
+    if (mask01 == 0.0f && g_tma_forward.load() && !g_force_general.load() && w % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         const int rc = launch_sep_fwd(p, y_dtype, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
@@ -200,10 +203,6 @@ int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const v
     CropParams p = base_params(n, k, c, h, w, oh, ow);
     p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.ggrid_up = ggrid_upstream;
     p.gtheta = gtheta; p.gx = gx; p.ggrid_out = ggrid_out;
-    if (mask01 == 0.0f && !g_force_general.load() && w % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        const int rc = launch_sep_bwd(p, gy_dtype, (cudaStream_t)stream);
-        if (rc >= 0) return rc;
-    }
     return launch_crop_bwd(p, gy_dtype, (cudaStream_t)stream);
 }
 

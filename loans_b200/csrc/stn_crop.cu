@@ -132,17 +132,21 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
 
     for (int c0 = 0; c0 < C; c0 += CG) {
         const int nc = EXACT ? CG : min(CG, C - c0);
-        {   // zero the tile
-            float4 *t4 = reinterpret_cast<float4 *>(tile);
-            const int n4 = CG * tile_plane / 4;
-            for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
+        bool touched = false;                                                  // warp-uniform
         for (int kk = 0; kk < p.K; ++kk) {
             const ScatterGeom &g = geom[kk];
             if (g.P == 0) continue;                                            // gather fallback crop
+            // cheap reject first: the crop's frame bounding box against the tile
+            if (g.r_max < r0 || g.r_min >= r0 + tr || g.s_max < s0 || g.s_min >= s0 + tw) continue;
             int i_lo, i_hi, j_lo, j_hi;
             if (!scatter_box(g, r0, tr, s0, tw, p.oH, p.oW, i_lo, i_hi, j_lo, j_hi)) continue;
+            if (!touched) {                                                    // zero the tile on first use only
+                float4 *t4 = reinterpret_cast<float4 *>(tile);
+                const int n4 = CG * tile_plane / 4;
+                for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                touched = true;
+            }
             const GT *gyc = gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
@@ -184,7 +188,22 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
         }
         // write the tile out: each gx element exactly once, zeros included
         float *gxb = p.gx + ((size_t)b * C + c0) * fpx;
-        if (p.gx_vec4 && !any_fallback) {
+        if (p.gx_vec4 && !any_fallback && !touched) {
+            // no crop reaches this tile: its gx is zero, written straight from registers
+            const int tw4 = tw >> 2;
+            const int total = tr * tw4;
+            int row = lane / tw4, c4 = lane - row * tw4;
+            const int drow = 32 / tw4, dc4 = 32 - drow * tw4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = lane; e < total; e += 32) {
+                float *gp = gxb + (size_t)(r0 + row) * p.W + s0 + 4 * c4;
+#pragma unroll
+                for (int ch = 0; ch < CG; ++ch)
+                    if (ch < nc) *reinterpret_cast<float4 *>(gp + (size_t)ch * fpx) = z;
+                row += drow; c4 += dc4;
+                if (c4 >= tw4) { c4 -= tw4; ++row; }
+            }
+        } else if (p.gx_vec4 && !any_fallback) {
             const int tw4 = tw >> 2;                                           // tw % 4 == 0 guaranteed by the host
             const int total = tr * tw4;
             int row = lane / tw4, c4 = lane - row * tw4;
@@ -203,6 +222,12 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
                 if (c4 >= tw4) { c4 -= tw4; ++row; }
             }
         } else {
+            if (!touched) {
+                float4 *t4 = reinterpret_cast<float4 *>(tile);
+                const int n4 = CG * tile_plane / 4;
+                for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+            }
             gx_writeout_slow<GT, CG>(p, xs, ys, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
         }
         __syncwarp();

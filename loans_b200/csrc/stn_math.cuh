@@ -330,6 +330,7 @@ struct ScatterGeom {
     float i00, i01, i10, i11;           // its inverse
     float slack;                        // pre-test slack in px
     int P, Q;                           // phase periods; P == 0 -> use the gather fallback for this crop
+    int r_min, r_max, s_min, s_max;     // unpadded frame rows / columns any tap of this crop can touch (conservative)
 };
 
 constexpr int kMaxScatterPhases = 64;
@@ -349,6 +350,16 @@ STN_HD ScatterGeom make_scatter_geom(const Theta &th, int H, int W, int oH, int 
     g.slack = 0.05f + 1e-5f * mag;
     const float det = g.muj * g.mvi - g.mui * g.mvj;
     const float scale = fabsf(g.muj * g.mvi) + fabsf(g.mui * g.mvj);
+    {   // bounding box of the four crop corners in padded pixel coordinates, widened by 2 px + slack
+        const float au = fabsf(g.muj) * nj, bu = fabsf(g.mui) * ni, av = fabsf(g.mvj) * nj, bv = fabsf(g.mvi) * ni;
+        const float u_lo = g.cu + fminf(g.muj * nj, 0.0f) + fminf(g.mui * ni, 0.0f), v_lo = g.cv + fminf(g.mvj * nj, 0.0f) + fminf(g.mvi * ni, 0.0f);
+        const float m = 2.0f + g.slack;
+        const float fs0 = fmaxf(u_lo - m - 1.0f, -1.0f), fs1 = fminf(u_lo + au + bu + m, 2.0e9f);
+        const float fr0 = fmaxf(v_lo - m - 1.0f, -1.0f), fr1 = fminf(v_lo + av + bv + m, 2.0e9f);
+        const bool ok = mag < 1e8f;                      // otherwise: no restriction
+        g.s_min = ok ? f_floor_i(fs0) : -1; g.s_max = ok ? f_ceil_i(fs1) : 0x7fffffff;
+        g.r_min = ok ? f_floor_i(fr0) : -1; g.r_max = ok ? f_ceil_i(fr1) : 0x7fffffff;
+    }
     g.P = 0; g.Q = 0;
     g.i00 = g.i01 = g.i10 = g.i11 = 0.0f;
     if (fabsf(det) > 1e-5f * scale + 1e-20f && mag < 1e6f) {

@@ -141,6 +141,7 @@ long long emu_gx_scatter(const float *theta, float mask01, const float *gy, floa
                 for (int kk = 0; kk < k; ++kk) {
                     const ScatterGeom &g = geom[kk];
                     if (g.P == 0) continue;
+                    if (g.r_max < r0 || g.r_min >= r0 + tr || g.s_max < s0 || g.s_min >= s0 + tw) continue;   // as the kernel
                     int i_lo, i_hi, j_lo, j_hi;
                     if (!scatter_box(g, r0, tr, s0, tw, oh, ow, i_lo, i_hi, j_lo, j_hi)) continue;
                     const float *gyc = gy + (size_t)(f * k + kk) * c * npx;

@@ -202,7 +202,7 @@ def test_golden_fixture_on_device(G):
 
 @pytest.mark.parametrize("name,batch", [("cfg1", None), ("cfg2", 16), ("cfg3", 6), ("cfg4", 3)])
 def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
-    """mask01 == 0 selects the table + TMA-staged kernels; LOANS_STN_CFG_FORCE_GENERAL switches them off."""
+    """LOANS_STN_CFG_TMA_FORWARD routes axis-aligned crops (mask01 == 0) through the table + TMA-staged forward."""
     from loans_b200 import _lib
     wl = W.WORKLOADS[name]
     d = W.make_inputs(wl, batch=batch, rotate=True, with_ggrid=True)
@@ -210,14 +210,16 @@ def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
     d["theta"][1::7, 0, 0] *= -1.0                    # mirrored crops
     osz = (wl.out_h, wl.out_w)
     k = wl.crops_per_frame
+    y0, g0 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+    b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    n0 = _lib.launch_count()
     try:
-        _lib.force_general(True)
-        y0, g0 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
-        b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+        _lib.tma_forward(True)
+        y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+        b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
     finally:
-        _lib.force_general(False)
-    y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
-    b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+        _lib.tma_forward(False)
+    assert _lib.launch_count() - n0 == 2
     assert np.array_equal(y0, y1) and np.array_equal(g0, g1)
     assert np.array_equal(b0[2], b1[2])                                   # ggrid bit-exact
     assert G.rel_max(b1[1], b0[1]) <= 2e-6 and G.rel_max(b1[0], b0[0]) <= 1e-5
@@ -233,4 +235,9 @@ def test_axis_aligned_kernels_on_ragged_shapes(G, shape):
                       [[0.5, 0, 7.0], [0, 0.5, -9.0]], [[0.9, 0.1, 0.8], [0.05, -0.9, -0.7]], [[0, 0, 0.2], [0, 0, -0.3]],
                       [[40.0, 3.0, 0.5], [-2.0, 55.0, 0.1]]], np.float32)
     x = rng.random((len(theta), c, h, w), dtype=np.float32)
-    _full_check(G, x, theta, (oh, ow), 0.0, 1, seed=7)
+    from loans_b200 import _lib
+    try:
+        _lib.tma_forward(True)
+        _full_check(G, x, theta, (oh, ow), 0.0, 1, seed=7)
+    finally:
+        _lib.tma_forward(False)
