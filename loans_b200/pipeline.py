@@ -1,0 +1,89 @@
+"""Host-buffer pipeline around the fused crop kernels: pinned host tensors in, pinned host tensors out.
+
+A LoANs-style consumer that keeps its frames on the host (the reference's ``prepare_images`` round-trips the whole
+batch through the host every step, sheep/sheep_localizer.py:72-82) pays PCIe for every step.  ``HostCropPipeline``
+hides as much of that as the link allows: ``depth`` sets of device buffers, three CUDA streams (H2D, compute, D2H)
+chained with events, so that the upload of step i+1 and the download of step i-1 run while step i computes --
+PCIe is full duplex.  The compute stream calls the C ABI directly (``loans_stn_crop_fwd`` / ``loans_stn_crop_bwd``).
+
+    pipe = HostCropPipeline(batch, channels, height, width, out_size, crops_per_frame=1, need_gx=True)
+    for step in ...:
+        pipe.submit(x_host, theta_host, gy_host, outputs)     # outputs: dict of pinned tensors y, grid, gtheta[, gx]
+    pipe.drain()                                              # every submitted step's outputs are now on the host
+
+All host tensors must be pinned (``tensor.pin_memory()``) for the copies to be asynchronous; they must stay alive and
+unmodified until ``drain()`` (or until ``depth`` further submits have been made).
+"""
+import torch
+
+from loans_b200 import _lib
+
+
+class HostCropPipeline(object):
+    def __init__(self, batch, channels, height, width, out_size, crops_per_frame=1, need_gx=True,
+                 out_dtype=torch.float32, depth=2, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HostCropPipeline needs a CUDA device (loans_b200 has no CPU fallback)")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dims = (int(batch), int(crops_per_frame), int(channels), int(height), int(width), int(out_size[0]), int(out_size[1]))
+        b, k, c, h, w, oh, ow = self.dims
+        n = b * k
+        self.need_gx = bool(need_gx)
+        self.dt = out_dtype
+        self.dt_code = _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32
+        self.depth = int(depth)
+        self.lib = _lib.lib()
+        with torch.cuda.device(self.dev):
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
+            self.slots = []
+            for _ in range(self.depth):
+                self.slots.append({
+                    "x": torch.empty((b, c, h, w), device=self.dev), "theta": torch.empty((n, 2, 3), device=self.dev),
+                    "gy": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
+                    "y": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
+                    "grid": torch.empty((n, 2, oh, ow), device=self.dev), "gtheta": torch.empty((n, 2, 3), device=self.dev),
+                    "gx": torch.empty((b, c, h, w), device=self.dev) if need_gx else None,
+                    "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_out": torch.cuda.Event(), "used": False})
+        self.step = 0
+        self.h2d_bytes = 4 * (b * c * h * w + n * 6) + n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4)
+        self.d2h_bytes = n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4) + 4 * (n * 2 * oh * ow + n * 6) \
+            + (4 * b * c * h * w if need_gx else 0)
+
+    def submit(self, x_host, theta_host, gy_host, outputs, mask01=0.0):
+        """Enqueue one fwd+bwd step.  ``outputs``: dict with pinned host tensors 'y', 'grid', 'gtheta' and, if need_gx, 'gx'."""
+        b, k, c, h, w, oh, ow = self.dims
+        n = b * k
+        s = self.slots[self.step % self.depth]
+        self.step += 1
+        with torch.cuda.device(self.dev):
+            with torch.cuda.stream(self.s_in):
+                if s["used"]:
+                    self.s_in.wait_event(s["ev_out"])            # the slot's previous results have left the device
+                s["x"].copy_(x_host, non_blocking=True)
+                s["theta"].copy_(theta_host, non_blocking=True)
+                s["gy"].copy_(gy_host, non_blocking=True)
+                s["ev_in"].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(s["ev_in"])
+                st = self.s_run.cuda_stream
+                p = lambda t: None if t is None else t.data_ptr()          # noqa: E731
+                _lib.check(self.lib.loans_stn_crop_fwd(p(s["x"]), p(s["theta"]), float(mask01), p(s["y"]), p(s["grid"]),
+                                                       n, k, c, h, w, oh, ow, self.dt_code, st), "loans_stn_crop_fwd")
+                _lib.check(self.lib.loans_stn_crop_bwd(p(s["x"]), p(s["theta"]), float(mask01), p(s["gy"]), None, p(s["gtheta"]),
+                                                       p(s["gx"]), None, n, k, c, h, w, oh, ow, self.dt_code, st),
+                           "loans_stn_crop_bwd")
+                s["ev_run"].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(s["ev_run"])
+                outputs["y"].copy_(s["y"], non_blocking=True)
+                outputs["grid"].copy_(s["grid"], non_blocking=True)
+                outputs["gtheta"].copy_(s["gtheta"], non_blocking=True)
+                if self.need_gx:
+                    outputs["gx"].copy_(s["gx"], non_blocking=True)
+                s["ev_out"].record(self.s_out)
+            s["used"] = True
+
+    def drain(self):
+        self.s_out.synchronize()
+        self.s_run.synchronize()
+        self.s_in.synchronize()

@@ -188,3 +188,27 @@ def test_type_checks_and_cpu_tensors_are_refused(T):
         spatial_transformer_sampler(x, T.zeros(2, 3, 4, 4, device="cuda"))
     with pytest.raises(ValueError):
         spatial_transformer_sampler(x, T.zeros(2, 2, 4, 4, device="cuda"), use_cudnn=True)
+
+
+def test_host_buffer_pipeline_matches_oracle(T):
+    """HostCropPipeline: pinned host in / out, three streams; four different batches in flight through two buffer sets."""
+    from loans_b200.pipeline import HostCropPipeline
+    wl = W.WORKLOADS["cfg1"]
+    osz = (wl.out_h, wl.out_w)
+    pipe = HostCropPipeline(3, 3, wl.height, wl.width, osz, need_gx=True, depth=2)
+    batches, outs = [], []
+    for i in range(4):
+        d = W.make_inputs(wl, seed=100 + i, batch=3)
+        batches.append(d)
+        h = {k: T.from_numpy(d[k]).pin_memory() for k in ("x", "theta", "gy")}
+        o = {"y": T.empty((3, 3) + osz).pin_memory(), "grid": T.empty((3, 2) + osz).pin_memory(),
+             "gtheta": T.empty((3, 2, 3)).pin_memory(), "gx": T.empty((3, 3, wl.height, wl.width)).pin_memory()}
+        outs.append((h, o))
+        pipe.submit(h["x"], h["theta"], h["gy"], o, mask01=0.0)
+    pipe.drain()
+    for d, (h, o) in zip(batches, outs):
+        y0, g0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+        gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], None, 0.0)
+        assert np.array_equal(o["y"].numpy(), y0) and np.array_equal(o["grid"].numpy(), g0)
+        assert np.abs(o["gx"].numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max()
+        assert np.abs(o["gtheta"].numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max()
