@@ -53,6 +53,55 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
     float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
     const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
 
+    if (EXACT) {
+        // one channel group covers all channels: two pixels per thread in flight -- both pixels' 8*CG tap loads are
+        // issued before either is interpolated, so a thread pays one memory round trip per PAIR of pixels
+        struct Px {
+            Weights4 wt;
+            float v[CG][4];
+            int q;
+            bool live;
+        };
+        auto prepare = [&](Px &px, const PxWalk &w) {
+            px.live = w.q < q_end;
+            px.q = w.q;
+            if (!px.live) return;
+            float g0, g1;
+            if (FROM_GRID) {
+                g0 = __ldg(gin + w.q);
+                g1 = __ldg(gin + npx + w.q);
+            } else {
+                const float xsj = xs[w.j], ysi = ys[w.i];
+                g0 = grid_elem(th.t00, th.t01, th.t02, xsj, ysi);
+                g1 = grid_elem(th.t10, th.t11, th.t12, xsj, ysi);
+                if (gout) {
+                    gout[w.q] = g0;
+                    gout[npx + w.q] = g1;
+                }
+            }
+            const Tap t = make_tap(g0, g1, p.H, p.W);
+            const TapAddr a = make_tap_addr(t, p.H, p.W);
+            px.wt = make_weights(t);
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) load_taps(xb + ch * plane, a, p.W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
+        };
+        auto finish = [&](const Px &px) {
+            if (!px.live) return;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch)
+                Elem<YT>::store(yb + px.q, ch * npx, interp(px.wt, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]));
+        };
+        PxWalk w(tile * p.px_per_cta + threadIdx.x, p.oW);
+        while (w.q < q_end) {
+            Px A, B;
+            prepare(A, w);
+            w.next();
+            prepare(B, w);
+            w.next();
+            finish(A);
+            finish(B);
+        }
+    } else {
     for (PxWalk w(tile * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
         float g0, g1;
         if (FROM_GRID) {
@@ -85,6 +134,7 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
         }
     }
 }
+}
 
 // ------------------------------------------------------------------------------------------ backward
 template <typename GT>
@@ -112,7 +162,7 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 // with __syncwarp() only.  The eight warps of a CTA take eight consecutive tiles of the same frame and share one
 // prologue (axis tables + per-crop geometry) behind the CTA's single barrier.
 template <typename GT, int CG, bool EXACT>
-__device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm,
+__device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, const bool any_fallback,
                                         const ScatterGeom *geom, float *tiles)
 {
     const int C = EXACT ? CG : p.C;
@@ -128,7 +178,6 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
     float *tile = tiles + warp * (CG * tile_plane);
     const int npx = p.oH * p.oW, fpx = p.H * p.W;
     const GT *gy = reinterpret_cast<const GT *>(p.gy);
-    const bool any_fallback = sm.flags[0] != 0;
 
     for (int c0 = 0; c0 < C; c0 += CG) {
         const int nc = EXACT ? CG : min(CG, C - c0);
@@ -279,24 +328,21 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
     fill_axis_tables(p, xs, ys);
     if (gx_cta) {
-        // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop
+        // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop.  The
+        // CTA's single barrier also tells everybody whether any crop of the frame needs the fallback.
         const int b = blockIdx.x / p.gx_ctas_per_frame;
-        if (threadIdx.x == 0) sm.flags[0] = 0;
+        int fallback = 0;
         if (b < p.N / p.K)
-            for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
+            for (int kk = threadIdx.x; kk < p.K; kk += kThreads) {
                 geom[kk] = make_scatter_geom(load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01),
                                              p.H, p.W, p.oH, p.oW);
-    }
-    __syncthreads();
-    if (gx_cta) {
-        const int b = blockIdx.x / p.gx_ctas_per_frame;
+                fallback |= geom[kk].P == 0;
+            }
+        const int any_fallback = __syncthreads_or(fallback);
         if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
-        // (benign race: every thread that finds a fallback crop writes the same 1)
-        for (int kk = threadIdx.x; kk < p.K; kk += kThreads)
-            if (geom[kk].P == 0) sm.flags[0] = 1;
-        __syncthreads();
-        gx_role<GT, CG, EXACT>(p, xs, ys, sm, geom, tiles);
+        gx_role<GT, CG, EXACT>(p, xs, ys, any_fallback != 0, geom, tiles);
     } else {
+        __syncthreads();
         theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
     }
 }

@@ -58,6 +58,68 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
 
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#ifndef STN_THETA_ILP
+#define STN_THETA_ILP 1      // 2 = two pixels in flight per thread: measured slower here (register pressure)
+#endif
+    if (EXACT && STN_THETA_ILP == 2) {
+        // all channels in one group: two crop pixels per thread in flight (taps and gy of both requested before
+        // either is reduced), one memory round trip per pair of pixels
+        struct Px {
+            Tap t;
+            float v[CG][4], g[CG];
+            float xsj, ysi;
+            int q;
+            bool live;
+        };
+        auto prepare = [&](Px &px, const PxWalk &w) {
+            px.live = w.q < q_end;
+            px.q = w.q;
+            if (!px.live) return;
+            px.xsj = xs[w.j]; px.ysi = ys[w.i];
+            px.t = make_tap(grid_elem(th.t00, th.t01, th.t02, px.xsj, px.ysi),
+                            grid_elem(th.t10, th.t11, th.t12, px.xsj, px.ysi), p.H, p.W);
+            const TapAddr a = make_tap_addr(px.t, p.H, p.W);
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                load_taps(xb + ch * plane, a, p.W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
+                px.g[ch] = Elem<GT>::load(gyb + w.q, ch * npx);
+            }
+        };
+        auto finish = [&](const Px &px) {
+            if (!px.live) return;
+            float su = 0.f, sv = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                float gu, gv;
+                grad_uv(px.t, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3], gu, gv);
+                gu = f_mul(gu, px.g[ch]);
+                gv = f_mul(gv, px.g[ch]);
+                if (ch == 0) { su = gu; sv = gv; }
+                else { su = f_add(su, gu); sv = f_add(sv, gv); }              // numpy.sum over the channel axis
+            }
+            finish_grad_uv(px.t, p.H, p.W, su, sv);
+            if (ggo) {
+                ggo[px.q] = su;
+                ggo[npx + px.q] = sv;
+            }
+            if (ggu) {
+                su = f_add(su, __ldg(ggu + px.q));
+                sv = f_add(sv, __ldg(ggu + npx + px.q));
+            }
+            s[0] = fmaf(su, px.xsj, s[0]); s[1] = fmaf(su, px.ysi, s[1]); s[2] += su;
+            s[3] = fmaf(sv, px.xsj, s[3]); s[4] = fmaf(sv, px.ysi, s[4]); s[5] += sv;
+        };
+        PxWalk w(rank * p.px_per_cta + threadIdx.x, p.oW);
+        while (w.q < q_end) {
+            Px A, B;
+            prepare(A, w);
+            w.next();
+            prepare(B, w);
+            w.next();
+            finish(A);
+            finish(B);
+        }
+    } else {
     for (PxWalk w(rank * p.px_per_cta + threadIdx.x, p.oW); w.q < q_end; w.next()) {
         const float xsj = xs[w.j], ysi = ys[w.i];
         const Tap t = make_tap(grid_elem(th.t00, th.t01, th.t02, xsj, ysi),
@@ -98,6 +160,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
         }
         s[0] = fmaf(su, xsj, s[0]); s[1] = fmaf(su, ysi, s[1]); s[2] += su;
         s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
+    }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
