@@ -168,8 +168,11 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
     const int C = EXACT ? CG : p.C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.gx_ctas_per_frame;
-    const int tix = (blockIdx.x - b * p.gx_ctas_per_frame) * kWarps + warp;
-    if (tix >= p.gx_tiles_per_frame) return;                                   // warp-uniform; no CTA barrier below
+    // this warp's tiles: gx_tiles_per_warp of them, interleaved over the warps of the CTA (warp-uniform loop; no CTA
+    // barrier below)
+  for (int tt = 0; tt < p.gx_tiles_per_warp; ++tt) {
+    const int tix = ((blockIdx.x - b * p.gx_ctas_per_frame) * p.gx_tiles_per_warp + tt) * kWarps + warp;
+    if (tix >= p.gx_tiles_per_frame) return;
     const int ty = tix / p.gx_tiles_x, tx = tix - ty * p.gx_tiles_x;
     const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
     const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
@@ -281,6 +284,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
         }
         __syncwarp();
     }
+  }
 }
 
 // Scalar write-out of a warp's tile, plus -- for crops whose transform is too degenerate for the phased scatter --
@@ -462,7 +466,19 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         p.gx_tiles_x = (p.W + tw - 1) / tw;
         const int tiles_y = (p.H + tr - 1) / tr;
         p.gx_tiles_per_frame = p.gx_tiles_x * tiles_y;
-        p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps - 1) / kWarps;
+        // tiles per warp: one while the batch is small (every CTA is resident at once and latency rules), more as the
+        // tile count grows, so that the per-CTA prologue (tables, geometry, barrier) is amortised over several tiles
+#ifndef STN_GX_MAX_TILES_PER_WARP
+#define STN_GX_MAX_TILES_PER_WARP 8
+#endif
+        {
+            const long long all_tiles = (long long)(p.N / p.K) * p.gx_tiles_per_frame;
+            long long tpw = all_tiles / ((long long)kWarps * kNumSMs * 6 * p.K);     // K crops per frame: K times the work per tile
+            if (tpw < 1) tpw = 1;
+            if (tpw > STN_GX_MAX_TILES_PER_WARP) tpw = STN_GX_MAX_TILES_PER_WARP;
+            p.gx_tiles_per_warp = (int)tpw;
+        }
+        p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps * p.gx_tiles_per_warp - 1) / (kWarps * p.gx_tiles_per_warp);
         p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * tw * kWarps);
         p.gx_vec4 = (p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
         const long long n_gx = (long long)(p.N / p.K) * p.gx_ctas_per_frame;
