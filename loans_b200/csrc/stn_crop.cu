@@ -143,7 +143,7 @@ struct GyLoader {
 };
 
 #ifndef STN_BWD_MIN_CTAS
-#define STN_BWD_MIN_CTAS 3
+#define STN_BWD_MIN_CTAS 4
 #endif
 
 // e / d for 0 <= e < 2^20 via one multiply (exact there: |error| <= 1.2e-7 * (e/d) < 0.5/d), integer division beyond
@@ -443,8 +443,11 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     const long long npx = (long long)p.oH * p.oW;
     const int cgsel = pick_channel_group(p.C);
     // cluster size: enough theta-role CTAs to occupy the machine twice over, 8 (portable maximum) at most
+#ifndef STN_THETA_CS_MAX
+#define STN_THETA_CS_MAX 4
+#endif
     unsigned cs = 1;
-    while (cs < 8 && (long long)p.N * cs < 2LL * kNumSMs && npx / (2 * cs) >= kThreads / 2) cs *= 2;
+    while (cs < STN_THETA_CS_MAX && (long long)p.N * cs < 2LL * kNumSMs && npx / (2 * cs) >= kThreads / 2) cs *= 2;
     p.ctas_per_crop = (int)cs;
     p.px_per_cta = (int)((npx + cs - 1) / cs);
     const long long theta_ctas = (long long)p.N * cs;
