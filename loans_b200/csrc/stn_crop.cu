@@ -22,6 +22,9 @@
 //     per-CTA partials through distributed shared memory in a fixed order: deterministic, no atomics, no
 //     zero-initialised output, no workspace.
 #include <cooperative_groups.h>
+#include <cuda.h>             // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
+#include <cstring>
 
 #include "stn_common.cuh"
 #include "stn_theta_role.cuh"
@@ -162,8 +165,8 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 // with __syncwarp() only.  The eight warps of a CTA take eight consecutive tiles of the same frame and share one
 // prologue (axis tables + per-crop geometry) behind the CTA's single barrier.
 template <typename GT, int CG, bool EXACT>
-__device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, const float *ys, const bool any_fallback,
-                                        const ScatterGeom *geom, float *tiles)
+__device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *gx_map, const float *xs, const float *ys,
+                                        const bool any_fallback, const ScatterGeom *geom, float *tiles)
 {
     const int C = EXACT ? CG : p.C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +175,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
     // barrier below)
   for (int tt = 0; tt < p.gx_tiles_per_warp; ++tt) {
     const int tix = ((blockIdx.x - b * p.gx_ctas_per_frame) * p.gx_tiles_per_warp + tt) * kWarps + warp;
-    if (tix >= p.gx_tiles_per_frame) return;
+    if (tix >= p.gx_tiles_per_frame) break;
     const int ty = tix / p.gx_tiles_x, tx = tix - ty * p.gx_tiles_x;
     const int r0 = ty * p.gx_tile_rows, s0 = tx * p.gx_tile_cols;
     const int tr = min(p.gx_tile_rows, p.H - r0), tw = min(p.gx_tile_cols, p.W - s0);
@@ -205,9 +208,10 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
             for (int cp = 0; cp < P; ++cp)
                 for (int cq = 0; cq < Q; ++cq) {
                     // phase (cp, cq): crop pixels with i == cp (mod P), j == cq (mod Q), dealt to the 32 lanes
-                    const int ia = first_congruent(i_lo, cp, P), ja = first_congruent(j_lo, cq, Q);
-                    const int nrows = ia <= i_hi ? (i_hi - ia) / P + 1 : 0;
-                    const int ncols = ja <= j_hi ? (j_hi - ja) / Q + 1 : 0;
+                    const bool one = (P | Q) == 1;                              // down-sampling by >= 2: the usual case
+                    const int ia = one ? i_lo : first_congruent(i_lo, cp, P), ja = one ? j_lo : first_congruent(j_lo, cq, Q);
+                    const int nrows = one ? i_hi - i_lo + 1 : (ia <= i_hi ? (i_hi - ia) / P + 1 : 0);
+                    const int ncols = one ? j_hi - j_lo + 1 : (ja <= j_hi ? (j_hi - ja) / Q + 1 : 0);
                     const int total = nrows * ncols;
                     const bool small = total < (1 << 20);
                     const float inv_nc = 1.0f / (float)max(ncols, 1);
@@ -255,6 +259,20 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
                 row += drow; c4 += dc4;
                 if (c4 >= tw4) { c4 -= tw4; ++row; }
             }
+        } else if (p.gx_tma_store && !any_fallback) {
+            // TMA tensor store: gx is described to the TMA unit as a (W, H, B*C) tensor with a (tile_cols, tile_rows, 1)
+            // box; one instruction per channel moves the whole tile from shared memory, clipped at the frame edges by
+            // the hardware.  The warp only waits until the tile has been READ before reusing the shared memory.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy tile writes -> async proxy
+            __syncwarp();
+            if (lane < nc) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + lane * tile_plane);
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             ::"l"(gx_map), "r"(s0), "r"(r0), "r"(b * C + c0 + lane), "r"(src) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
         } else if (p.gx_vec4 && !any_fallback) {
             const int tw4 = tw >> 2;                                           // tw % 4 == 0 guaranteed by the host
             const int total = tr * tw4;
@@ -285,6 +303,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const float *xs, co
         __syncwarp();
     }
   }
+    if (p.gx_tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // this thread's tensor stores have landed
 }
 
 // Scalar write-out of a warp's tile, plus -- for crops whose transform is too degenerate for the phased scatter --
@@ -317,9 +336,9 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 }
 
 template <typename GT, int CG, bool EXACT>
-__global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p)
+__global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p, const __grid_constant__ CUtensorMap gx_map)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];       // TMA tensor stores read 128-byte aligned tiles
     // layout: [8 warp tiles (gx role only, 16 B aligned)] [BwdSmem] [xs | ys] [ScatterGeom[K]]
     float *tiles = reinterpret_cast<float *>(smem_raw);
     unsigned char *q = smem_raw + p.gx_tile_bytes;
@@ -344,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
             }
         const int any_fallback = __syncthreads_or(fallback);
         if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
-        gx_role<GT, CG, EXACT>(p, xs, ys, any_fallback != 0, geom, tiles);
+        gx_role<GT, CG, EXACT>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles);
     } else {
         __syncthreads();
         theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
@@ -401,7 +420,7 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
 }
 
 template <typename GT, int CG, bool EXACT>
-static cudaError_t launch_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+static cudaError_t launch_bwd_tt(const CropParams &p, const CUtensorMap &gx_map, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;                 // per template instance; only ever grows
@@ -423,18 +442,46 @@ static cudaError_t launch_bwd_tt(const CropParams &p, unsigned ctas, unsigned cs
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT>, p);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT>, p, gx_map);
 }
 
 template <typename GT>
-static cudaError_t launch_bwd_t(const CropParams &p, int cgsel, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+static cudaError_t launch_bwd_t(const CropParams &p, const CUtensorMap &m, int cgsel, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     const bool exact = p.C == cgsel;
     switch (cgsel) {
-    case 1: return launch_bwd_tt<GT, 1, true>(p, ctas, cs, smem, s);
-    case 3: return exact ? launch_bwd_tt<GT, 3, true>(p, ctas, cs, smem, s) : launch_bwd_tt<GT, 3, false>(p, ctas, cs, smem, s);
-    default: return exact ? launch_bwd_tt<GT, 4, true>(p, ctas, cs, smem, s) : launch_bwd_tt<GT, 4, false>(p, ctas, cs, smem, s);
+    case 1: return launch_bwd_tt<GT, 1, true>(p, m, ctas, cs, smem, s);
+    case 3: return exact ? launch_bwd_tt<GT, 3, true>(p, m, ctas, cs, smem, s) : launch_bwd_tt<GT, 3, false>(p, m, ctas, cs, smem, s);
+    default: return exact ? launch_bwd_tt<GT, 4, true>(p, m, ctas, cs, smem, s) : launch_bwd_tt<GT, 4, false>(p, m, ctas, cs, smem, s);
     }
+}
+
+// gx as a 3-D tensor (W, H, B*C) with a (tile_cols, tile_rows, 1) box for the TMA tensor stores of the gx role.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_gx_map(CUtensorMap *map, float *gx, int planes, int H, int W, int tile_rows, int tile_cols)
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)tile_cols, (cuuint32_t)tile_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, gx, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
@@ -452,6 +499,8 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     p.px_per_cta = (int)((npx + cs - 1) / cs);
     const long long theta_ctas = (long long)p.N * cs;
     long long gx_ctas = 0;
+    alignas(64) CUtensorMap gx_map;
+    memset(&gx_map, 0, sizeof(gx_map));
     size_t smem = sizeof(BwdSmem) + sizeof(float) * (size_t)((p.oW + p.oH + 1) & ~1);
     if (p.gx) {
         // one tile per warp: STN_GX_TILE_ROWS rows x (W cut evenly in pieces of <= STN_GX_TILE_COLS, multiple of 4)
@@ -484,6 +533,14 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps * p.gx_tiles_per_warp - 1) / (kWarps * p.gx_tiles_per_warp);
         p.gx_tile_bytes = (int)(sizeof(float) * (size_t)cgsel * tr * tw * kWarps);
         p.gx_vec4 = (p.W % 4 == 0 && (reinterpret_cast<uintptr_t>(p.gx) & 15) == 0) ? 1 : 0;
+        // TMA tensor store of the tiles: 16-byte aligned rows, 128-byte aligned channel planes in shared memory
+#ifndef STN_GX_TMA_STORE
+#define STN_GX_TMA_STORE 1
+#endif
+        p.gx_tma_store = 0;
+        if (STN_GX_TMA_STORE && p.gx_vec4 && tw <= 256 && tr <= 256 && ((size_t)tr * tw * sizeof(float)) % 128 == 0 &&
+            (long long)p.H * p.W * 4 < (1LL << 40))
+            p.gx_tma_store = encode_gx_map(&gx_map, p.gx, (p.N / p.K) * p.C, p.H, p.W, tr, tw) ? 1 : 0;
         const long long n_gx = (long long)(p.N / p.K) * p.gx_ctas_per_frame;
         if (n_gx > 0x3fffffffLL) return set_error("crop_bwd: too many gx CTAs (%lld)", n_gx);
         gx_ctas = ((n_gx + cs - 1) / cs) * cs;                                  // cluster boundaries stay on role boundaries
@@ -493,8 +550,8 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     const long long ctas = theta_ctas + gx_ctas;
     if (ctas > 0x7fffffffLL) return set_error("crop_bwd: too many CTAs (%lld)", ctas);
     if (smem > 200 * 1024) return set_error("crop_bwd: %d crops per frame need %zu B of shared memory (max 200 KiB)", p.K, smem);
-    cudaError_t e = gy_dtype == 0 ? launch_bwd_t<float>(p, cgsel, (unsigned)ctas, cs, smem, stream)
-                                  : launch_bwd_t<__nv_bfloat16>(p, cgsel, (unsigned)ctas, cs, smem, stream);
+    cudaError_t e = gy_dtype == 0 ? launch_bwd_t<float>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream)
+                                  : launch_bwd_t<__nv_bfloat16>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream);
     count_launch();
     if (e != cudaSuccess) return set_error("crop_bwd launch failed: %s", cudaGetErrorString(e));
     return 0;
