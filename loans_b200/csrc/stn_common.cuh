@@ -34,6 +34,7 @@ struct CropParams {
     int gx_tile_rows, gx_tile_cols, gx_tile_pitch, gx_tile_bytes;
     int gx_vec4;             // 128-bit stores of gx are legal (W % 4 == 0, aligned base)
     int gx_tma_store;        // tiles leave shared memory through TMA tensor stores (map passed next to this struct)
+    int gx_zero_bytes;       // one zero plane per CTA behind the tiles: source of the stores of untouched tiles
     // separable path (stn_separable.cu)
     int sep_rows, sep_pitch, sep_buf_offset, gx_tiles_per_warp;
 };

@@ -166,7 +166,7 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 // prologue (axis tables + per-crop geometry) behind the CTA's single barrier.
 template <typename GT, int CG, bool EXACT>
 __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *gx_map, const float *xs, const float *ys,
-                                        const bool any_fallback, const ScatterGeom *geom, float *tiles)
+                                        const bool any_fallback, const ScatterGeom *geom, float *tiles, const float *zero_plane)
 {
     const int C = EXACT ? CG : p.C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,7 +244,15 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
         }
         // write the tile out: each gx element exactly once, zeros included
         float *gxb = p.gx + ((size_t)b * C + c0) * fpx;
-        if (p.gx_vec4 && !any_fallback && !touched) {
+        if (p.gx_tma_store && !any_fallback && !touched) {
+            // no crop reaches this tile: its gx is zero -- one tensor store per channel from the CTA's zero plane
+            if (lane < nc) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(zero_plane);
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             ::"l"(gx_map), "r"(s0), "r"(r0), "r"(b * C + c0 + lane), "r"(src) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else if (p.gx_vec4 && !any_fallback && !touched) {
             // no crop reaches this tile: its gx is zero, written straight from registers
             const int tw4 = tw >> 2;
             const int total = tr * tw4;
@@ -341,7 +349,8 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     extern __shared__ __align__(128) unsigned char smem_raw[];       // TMA tensor stores read 128-byte aligned tiles
     // layout: [8 warp tiles (gx role only, 16 B aligned)] [BwdSmem] [xs | ys] [ScatterGeom[K]]
     float *tiles = reinterpret_cast<float *>(smem_raw);
-    unsigned char *q = smem_raw + p.gx_tile_bytes;
+    float *zero_plane = reinterpret_cast<float *>(smem_raw + p.gx_tile_bytes);           // gx role, TMA path only
+    unsigned char *q = smem_raw + p.gx_tile_bytes + p.gx_zero_bytes;
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(q);
     q += sizeof(BwdSmem);
     float *xs = reinterpret_cast<float *>(q);
@@ -350,6 +359,11 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
     const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
     fill_axis_tables(p, xs, ys);
+    if (gx_cta && p.gx_zero_bytes) {
+        float4 *z4 = reinterpret_cast<float4 *>(zero_plane);
+        for (int e = threadIdx.x; e < p.gx_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (gx_cta) {
         // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop.  The
         // CTA's single barrier also tells everybody whether any crop of the frame needs the fallback.
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
             }
         const int any_fallback = __syncthreads_or(fallback);
         if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
-        gx_role<GT, CG, EXACT>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles);
+        gx_role<GT, CG, EXACT>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles, zero_plane);
     } else {
         __syncthreads();
         theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
@@ -544,7 +558,8 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         const long long n_gx = (long long)(p.N / p.K) * p.gx_ctas_per_frame;
         if (n_gx > 0x3fffffffLL) return set_error("crop_bwd: too many gx CTAs (%lld)", n_gx);
         gx_ctas = ((n_gx + cs - 1) / cs) * cs;                                  // cluster boundaries stay on role boundaries
-        smem += (size_t)p.gx_tile_bytes + sizeof(ScatterGeom) * (size_t)p.K;
+        p.gx_zero_bytes = p.gx_tma_store ? (int)(sizeof(float) * (size_t)tr * tw) : 0;
+        smem += (size_t)p.gx_tile_bytes + p.gx_zero_bytes + sizeof(ScatterGeom) * (size_t)p.K;
     }
     p.gx_ctas = (int)gx_ctas;
     const long long ctas = theta_ctas + gx_ctas;
