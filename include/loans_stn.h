@@ -52,9 +52,20 @@ unsigned long long loans_stn_launch_count(void);
  * LOANS_STN_CFG_TMA_FORWARD != 0: forward of axis-aligned crops (mask01 == 0, w % 4 == 0) through the AxisTap-table +
  *   TMA-bulk-copy-staged kernel (stn_separable.cu) instead of the direct gather.  Default 0: on B200 the direct gather
  *   measured faster at every BASELINE size (profiles/README.md).
- * LOANS_STN_CFG_FORCE_GENERAL != 0: never take the axis-aligned kernel, whatever the other switch says. */
+ * LOANS_STN_CFG_FORCE_GENERAL != 0: never take an axis-aligned kernel, whatever the other switches say.
+ * LOANS_STN_CFG_BAND_BACKWARD: backward of axis-aligned crops (mask01 == 0, one crop per frame, gx wanted, w % 4 == 0)
+ *   through the band kernel (stn_band.cu).  -1 (default): where it measured faster (frame rows of >= 4 KiB, e.g. 512-px
+ *   frames), 1: whenever it applies, 0: never.  gx, ggrid: same values; gtheta: same sums in a different order (both
+ *   within the 1e-4 bar).
+ * LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: tuning knobs of the band kernel for A/B measurements
+ *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant); 0 = automatic. */
 #define LOANS_STN_CFG_FORCE_GENERAL 1
 #define LOANS_STN_CFG_TMA_FORWARD 2
+#define LOANS_STN_CFG_BAND_BACKWARD 3
+#define LOANS_STN_CFG_BAND_CS 4
+#define LOANS_STN_CFG_BAND_ROWS 5
+#define LOANS_STN_CFG_BAND_TILE_KB 6
+#define LOANS_STN_CFG_BAND_VARIANT 7
 int loans_stn_configure(int key, int value);
 
 /* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.

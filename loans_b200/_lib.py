@@ -12,6 +12,8 @@ ABI_VERSION = 1
 F32, BF16 = 0, 1
 CFG_FORCE_GENERAL = 1
 CFG_TMA_FORWARD = 2
+CFG_BAND_BACKWARD = 3
+CFG_BAND_CS, CFG_BAND_ROWS, CFG_BAND_TILE_KB, CFG_BAND_VARIANT = 4, 5, 6, 7
 
 _lib = None
 
@@ -72,6 +74,18 @@ def force_general(on):
 def tma_forward(on):
     """Opt into the TMA-staged forward kernel for axis-aligned crops (mask01 == 0)."""
     check(lib().loans_stn_configure(CFG_TMA_FORWARD, int(bool(on))), "loans_stn_configure")
+
+
+def band_backward(on):
+    """Backward of axis-aligned crops through the band kernel: True = whenever it applies, False = never (always the
+    general kernel), None = the library default (by shape: wide frame rows)."""
+    check(lib().loans_stn_configure(CFG_BAND_BACKWARD, -1 if on is None else int(bool(on))), "loans_stn_configure")
+
+
+def band_tuning(cs=0, rows=0, tile_kb=0, variant=0):
+    """A/B knobs of the band kernel (0 = automatic): CTAs per crop, crop rows per band, tile budget, kernel variant."""
+    for key, val in ((CFG_BAND_CS, cs), (CFG_BAND_ROWS, rows), (CFG_BAND_TILE_KB, tile_kb), (CFG_BAND_VARIANT, variant)):
+        check(lib().loans_stn_configure(key, int(val)), "loans_stn_configure")
 
 
 def launch_count():

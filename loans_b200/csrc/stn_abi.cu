@@ -36,10 +36,13 @@ int launch_grid_bwd(const float *ggrid, float *gtheta, int n, int oh, int ow, cu
 int launch_sampler_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stream);
 int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
-int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);      // -1: shape not supported, use the general kernel
+int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
+int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not a band shape, use the general kernel
+void band_tuning(int which, int value);      // -1: shape not supported, use the general kernel
 
 static std::atomic<int> g_force_general{0};
 static std::atomic<int> g_tma_forward{0};
+static std::atomic<int> g_band_backward{-1};    // -1: by shape (wide frame rows), 0: never, 1: whenever it applies
 
 static int need_device(const char *what)
 {
@@ -99,6 +102,12 @@ int loans_stn_configure(int key, int value)
 {
     if (key == LOANS_STN_CFG_FORCE_GENERAL) { g_force_general.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_TMA_FORWARD) { g_tma_forward.store(value != 0); return 0; }
+    if (key == LOANS_STN_CFG_BAND_BACKWARD) { g_band_backward.store(value < 0 ? -1 : (value != 0)); return 0; }
+    if (key >= LOANS_STN_CFG_BAND_CS && key <= LOANS_STN_CFG_BAND_VARIANT) {
+        if (value < 0) return set_error("loans_stn_configure: key %d needs a value >= 0", key);
+        band_tuning(key - LOANS_STN_CFG_BAND_CS, value);
+        return 0;
+    }
     return set_error("loans_stn_configure: unknown key %d", key);
 }
 
@@ -203,6 +212,17 @@ int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const v
     CropParams p = base_params(n, k, c, h, w, oh, ow);
     p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.ggrid_up = ggrid_upstream;
     p.gtheta = gtheta; p.gx = gx; p.ggrid_out = ggrid_out;
+    // mask01 == 0 (LoANs' ratio = 0.0), one crop per frame, gx wanted: the band backward -- every crop pixel evaluated
+    // once, gx written once by the band that owns the frame rows (stn_band.cu); crops it declines run the general roles
+    // inside the same launch.  Measured on B200 (profiles/README.md) it wins where frame rows are wide (512-px frames:
+    // 192 vs 209 us at BASELINE config 3), ties at config 2 and loses at config 5, so by default it is taken for frame
+    // rows of at least 4 KiB per channel group; LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on / off.
+    const int band = g_band_backward.load();
+    const bool band_shape = (long long)w * c * (long long)sizeof(float) >= 4096;
+    if (mask01 == 0.0f && k == 1 && gx != nullptr && (band == 1 || (band < 0 && band_shape)) && !g_force_general.load()) {
+        const int rc = launch_crop_bwd_band(p, gy_dtype, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     return launch_crop_bwd(p, gy_dtype, (cudaStream_t)stream);
 }
 

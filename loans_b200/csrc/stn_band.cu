@@ -1,0 +1,477 @@
+// stn_band.cu -- the backward LoANs actually runs, in one pass over the crop pixels.
+//
+// LoANs calls rotation_dropout(..., ratio=0.0) in front of the grid (reference sheep/sheep_localizer.py:61,169), so
+// mask01 == 0 and every crop is an upright box: u depends on the crop column only, v on the crop row only.  For that
+// case (one crop per frame, the only thing Chainer's sampler has) the gradient of the frame splits by crop rows, and
+// a thread-block CLUSTER per crop does the whole backward with every crop pixel evaluated exactly ONCE:
+//
+//   * a CTA takes a run of crop rows and works through it in BANDS (stn_band_plan.cuh).  A band owns the frame rows
+//     between the first row it touches and the first row the next band touches: the bands of a crop partition the
+//     frame, so gx is written exactly once, zeros included -- no memset pass, no atomics, bit-reproducible;
+//   * per crop pixel: 4 taps x C channels + gy -> d/du, d/dv (bit-exact with the oracle) accumulated into the six
+//     gtheta sums, and gy * wu * wv added into the band's shared-memory tile of frame rows.  Column / row
+//     coordinate chains come from BandAxis tables built once per CTA (oW + rows entries instead of one chain per
+//     pixel).  When the crop steps by less than ~2 frame pixels the adds run in P * Q conflict-free phases;
+//   * the tile rows leave shared memory as TMA bulk copies (cp.async.bulk.global.shared::cta, SASS UBLKCP), whole
+//     frame rows at a time; the untouched frame rows between, above and below them are bulk-copied from a zero
+//     plane, issued BEFORE the pixel work so the TMA unit streams them out while the SM computes;
+//   * gtheta: warp shuffles + shared memory, then cluster rank 0 adds the per-CTA partials over distributed shared
+//     memory in rank order (reduce_gtheta, stn_theta_role.cuh).
+//
+// Crops the plan declines (mirrored boxes, up-sampling by more than kBandMaxPhases, non-finite theta) are handled in
+// the same launch by the same cluster running the general roles (stn_gx_role.cuh, stn_theta_role.cuh).
+#include <cooperative_groups.h>
+
+#include "stn_band_plan.cuh"
+#include "stn_common.cuh"
+#include "stn_gx_role.cuh"
+#include "stn_theta_role.cuh"
+
+namespace stn {
+
+
+#ifdef STN_BAND_TRACE
+// debug build only: per-CTA timestamps (globaltimer ns) at the stages of the band kernel, 16 slots per CTA
+__device__ long long *g_band_trace = nullptr;
+__device__ __forceinline__ void trace(int slot)
+{
+    if (threadIdx.x == 0 && g_band_trace) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_band_trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
+#define TRACE(k) trace(k)
+#else
+#define TRACE(k)
+#endif
+
+__device__ __forceinline__ void bulk_s2g(float *dst, const float *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// A crop the band plan declines: the cluster runs the general roles on it (tiles over the whole frame, then gtheta).
+template <typename GT, int CG>
+__device__ __noinline__ void band_declined(const CropParams &p, const Theta &th, unsigned char *smem_raw, BwdSmem &sm,
+                                           float *xs, float *ys, ScatterGeom *geom, int n, int rank)
+{
+    fill_axis_tables(p, xs, ys);
+    int fb = 0;
+    if (threadIdx.x == 0) {
+        geom[0] = make_scatter_geom(th, p.H, p.W, p.oH, p.oW);
+        fb = geom[0].P == 0;
+    }
+    const int any_fb = __syncthreads_or(fb);
+    gx_role<GT, CG, true>(p, nullptr, xs, ys, any_fb != 0, geom, reinterpret_cast<float *>(smem_raw), nullptr, n, rank,
+                          p.band_fb_tiles_per_warp);
+    theta_role<GT, CG, true>(p, xs, ys, sm, (int)blockIdx.x);
+}
+
+// ILP = crop pixels in flight per thread, MINB = CTAs per SM the register budget is set for
+template <typename GT, int CG, int ILP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __grid_constant__ CropParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [tile | zero plane] (the general roles' warp tiles alias it) [BwdSmem] [coltab] [rowtab] [rowslot] [xs|ys] [geom]
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    float *zero_plane = reinterpret_cast<float *>(smem_raw + p.band_tile_bytes);
+    unsigned char *q = smem_raw + p.band_region_bytes;
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(q);
+    q += sizeof(BwdSmem);
+    BandAxis *coltab = reinterpret_cast<BandAxis *>(q);
+    q += sizeof(BandAxis) * p.oW;
+    BandAxis *rowtab = reinterpret_cast<BandAxis *>(q);
+    q += sizeof(BandAxis) * p.band_tab_rows;
+    int2 *rowslot = reinterpret_cast<int2 *>(q);
+    q += sizeof(int2) * p.band_tab_rows;
+    float *xs = reinterpret_cast<float *>(q);
+    float *ys = xs + p.oW;
+    q += sizeof(float) * ((p.oW + p.oH + 3) & ~3);
+    ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
+
+    TRACE(0);
+    const int cs = p.ctas_per_crop;
+    const int n = blockIdx.x / cs, rank = blockIdx.x - n * cs;
+    const int tid = threadIdx.x;
+    {   // this CTA's gy rows do not depend on theta: start them towards L2 while theta is on its way
+        const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
+        const int row_elems = max(r1 - r0, 0) * p.oW;
+        const int lines = (row_elems * (int)sizeof(GT) + 127) / 128;
+        for (int e = tid; e < lines * CG; e += kThreads) {
+            const int ch = e / lines, l = e - ch * lines;
+            const char *a = reinterpret_cast<const char *>(reinterpret_cast<const GT *>(p.gy) + ((size_t)n * CG + ch) * p.oH * p.oW +
+                                                           (size_t)r0 * p.oW) + (size_t)l * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
+    const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
+    const BandCrop bc = make_band_crop(th, p.H, p.W, p.oH, p.oW);     // the same verdict in every CTA of the cluster
+    if (!bc.ok) {
+        band_declined<GT, CG>(p, th, smem_raw, sm, xs, ys, geom, n, rank);
+        return;
+    }
+    TRACE(1);
+    const int H = p.H, W = p.W, oH = p.oH, oW = p.oW;
+    const int P = bc.P, Q = bc.Q;
+    const int i0 = rank * p.band_rows_cta, i1 = min(oH, i0 + p.band_rows_cta);
+    const int t0 = max(i0 - (P - 1), 0), t1 = min(i1 + 1, oH);
+    // ---- prologue: coordinate chains once per crop column / row, zero plane
+    for (int k = tid; k < oW; k += kThreads) coltab[k] = make_band_axis(th.t00, th.t01, th.t02, lin_x_at(p, k), true, W);
+    for (int k = tid; k < t1 - t0; k += kThreads)
+        rowtab[k] = make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, t0 + k), false, H);
+    if (tid >= kThreads - 2) {                                        // first and last frame row the crop touches: L, E
+        const int last = tid == kThreads - 1;
+        int lo, hi;
+        band_row_range(make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, last ? oH - 1 : 0), false, H), H, lo, hi);
+        sm.flags[last] = last ? hi : lo;
+    }
+    {
+        float4 *z4 = reinterpret_cast<float4 *>(zero_plane);
+        for (int e = tid; e < p.band_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_async_smem();
+    }
+    __syncthreads();
+    TRACE(2);
+    if (!(p.band_flags & 2) && i0 < i1) {
+        // every frame row segment this CTA will gather from, requested into L2 now, in one go, before any CTA has started to
+        // store: gx is bound by the DRAM write rate, and a load that queues behind a burst of stores waits for the whole burst
+        const int ua = (coltab[0].code & kAxIdxMask) - 1, ub = (coltab[oW - 1].code & kAxIdxMask);
+        const int c_lo = max(ua, 0) & ~31, c_hi = min(ub, W - 1);                  // columns, 128-byte lines
+        const int lines = c_hi >= c_lo ? (c_hi - c_lo) / 32 + 1 : 0;
+        const int nrow2 = 2 * (i1 - t0);                                            // two tap rows per crop row (halo included)
+        const float *xn = p.x + (size_t)n * CG * ((size_t)H * W);
+        for (int e = tid; e < nrow2 * lines * CG; e += kThreads) {
+            const int l = e % lines, rc = e / lines;
+            const int ch = rc % CG, r2 = rc / CG;
+            const int fr = (rowtab[r2 >> 1].code & kAxIdxMask) - 1 + (r2 & 1);
+            if (fr >= 0 && fr < H) {
+                const float *a = xn + (size_t)ch * H * W + (size_t)fr * W + c_lo + 32 * l;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
+
+    const int npx = oH * oW;
+    const int plane = H * W;
+    const size_t fpx = (size_t)plane;
+    const float *xb = p.x + (size_t)n * CG * fpx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * CG * npx;
+    float *gxb = p.gx + (size_t)n * CG * fpx;
+    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
+    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
+    const int tile_plane = p.band_cap * W;                            // floats per channel of the tile
+    const int zrows = p.band_zero_bytes / (W * 4);
+    const float inv_ow = 1.0f / (float)oW;
+    const int nphases = P * Q;
+
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int warp = tid >> 5, lane = tid & 31;
+    bool pending = false;                                             // tile stores of the previous band in flight
+    struct Px {
+        float v[CG][4], g[CG];
+        int i, j;
+        bool live;
+    };
+    for (int a = i0; a < i1;) {
+        const BandPlan pl = plan_band(rowtab, t0, a, i1, oH, H, P, p.band_cap, p.band_rows, sm.flags[1]);
+        const int nspans = band_span_count(pl);
+        const int npxb = (pl.b - pl.h) * oW;
+        auto prepare = [&](Px &px, int e) {
+            px.live = e < npxb;
+            if (!px.live) return;
+            const int ri = __float2int_rz(((float)e + 0.5f) * inv_ow);
+            px.i = pl.h + ri;
+            px.j = e - ri * oW;
+            const int u0 = coltab[px.j].code & kAxIdxMask, v0 = rowtab[px.i - t0].code & kAxIdxMask;
+            TapAddr ta;
+            ta.c0 = u0 >= 1; ta.c1 = u0 <= W - 1; ta.r0 = v0 >= 1; ta.r1 = v0 <= H - 1;
+            ta.o00 = (v0 - 1) * W + (u0 - 1);
+            const GT *gp = gyb + px.i * oW + px.j;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                load_taps(xb + ch * plane, ta, W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
+                px.g[ch] = Elem<GT>::load(gp, ch * npx);
+            }
+        };
+        auto reduce = [&](const Px &px) {                             // gtheta sums and ggrid: own rows only
+            if (!px.live || px.i < pl.a) return;
+            const BandAxis col = coltab[px.j], row = rowtab[px.i - t0];
+            const Tap t = tap_from_band_axes(col, row, H, W);
+            float su = 0.f, sv = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                float gu, gv;
+                grad_uv(t, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3], gu, gv);
+                gu = f_mul(gu, px.g[ch]);
+                gv = f_mul(gv, px.g[ch]);
+                if (ch == 0) { su = gu; sv = gv; }
+                else { su = f_add(su, gu); sv = f_add(sv, gv); }      // numpy.sum over the channel axis
+            }
+            finish_grad_uv(t, H, W, su, sv);
+            const int qq = px.i * oW + px.j;
+            if (ggo) {
+                ggo[qq] = su;
+                ggo[npx + qq] = sv;
+            }
+            if (ggu) {
+                su = f_add(su, __ldg(ggu + qq));
+                sv = f_add(sv, __ldg(ggu + npx + qq));
+            }
+            s[0] = fmaf(su, col.lin, s[0]); s[1] = fmaf(su, row.lin, s[1]); s[2] += su;
+            s[3] = fmaf(sv, col.lin, s[3]); s[4] = fmaf(sv, row.lin, s[4]); s[5] += sv;
+        };
+        auto scatter = [&](const Px &px) {                            // gy * wu * wv into the tile, reference order
+            const int2 sl = rowslot[px.i - pl.h];
+            if (sl.x < 0 && sl.y < 0) return;
+            const BandAxis col = coltab[px.j], row = rowtab[px.i - t0];
+            const bool c0 = (col.code & kAxTap0) != 0, c1 = (col.code & kAxTap1) != 0;
+            float *tp = tile + ((col.code & kAxIdxMask) - 1);
+            float *r0p = tp + sl.x * W, *r1p = tp + sl.y * W;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                const float a1 = f_mul(px.g[ch], col.w1), a0 = f_mul(px.g[ch], col.w0);
+                if (sl.x >= 0) {
+                    if (c0) r0p[ch * tile_plane] = f_add(r0p[ch * tile_plane], f_mul(a1, row.w1));
+                    if (c1) r0p[ch * tile_plane + 1] = f_add(r0p[ch * tile_plane + 1], f_mul(a0, row.w1));
+                }
+                if (sl.y >= 0) {
+                    if (c0) r1p[ch * tile_plane] = f_add(r1p[ch * tile_plane], f_mul(a1, row.w0));
+                    if (c1) r1p[ch * tile_plane + 1] = f_add(r1p[ch * tile_plane + 1], f_mul(a0, row.w0));
+                }
+            }
+        };
+        auto zero_spans = [&]() {
+            for (int e = warp + kWarps * lane; e < ((nspans + 1) >> 1) * CG; e += kThreads) {
+                const int k = e / CG, ch = e - k * CG;
+                const BandSpan sp = band_span(pl, rowtab, t0, H, 2 * k);
+                float *dst = gxb + (size_t)ch * fpx + (size_t)sp.row * W;
+                for (int r = 0; r < sp.nrows; r += zrows)
+                    bulk_s2g(dst + (size_t)r * W, zero_plane, (uint32_t)(min(zrows, sp.nrows - r) * W * 4));
+            }
+        };
+        // (1) the first ILP crop pixels per thread: taps and gy requested before anything else (the band's latency)
+        Px px[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) prepare(px[u], u * kThreads + tid);
+        TRACE(3);
+        if (p.band_flags & 1) zero_spans();
+        if (pending) {                                                // the tile is free once the TMA unit has read it
+            bulk_wait_read();
+            __syncthreads();
+        }
+        // (3) zero the tile rows in use, tile slots of the crop rows
+        {
+            const int row4 = W >> 2, n4 = pl.nslots * row4;
+#pragma unroll
+            for (int ch = 0; ch < CG; ++ch) {
+                float4 *t4 = reinterpret_cast<float4 *>(tile + ch * tile_plane);
+                for (int e = tid; e < n4; e += kThreads) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int e = tid; e < pl.b - pl.h; e += kThreads) {
+                int s0, s1;
+                band_row_slots(pl, rowtab[pl.h + e - t0], pl.h + e, s0, s1);
+                rowslot[e] = make_int2(s0, s1);
+            }
+        }
+        __syncthreads();
+        TRACE(4);
+        // (4) the crop pixels of rows [h, b), ILP per thread in flight
+        for (int e0 = 0; e0 < npxb; e0 += ILP * kThreads) {
+            if (e0 > 0) {
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) prepare(px[u], e0 + u * kThreads + tid);
+            }
+            TRACE(5);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) reduce(px[u]);
+            TRACE(6);
+            if (nphases == 1) {
+#pragma unroll
+                for (int u = 0; u < ILP; ++u)
+                    if (px[u].live) scatter(px[u]);
+            } else {
+                // crop pixels of one phase never share a frame pixel; phases are separated by CTA barriers
+                for (int ph = 0; ph < nphases; ++ph) {
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u)
+                        if (px[u].live && (px[u].i % P) * Q + (px[u].j % Q) == ph) scatter(px[u]);
+                    __syncthreads();
+                }
+            }
+        }
+        // (5) tile rows -> gx.  A bulk copy is issued per lane (the warp serialises them): the ops are dealt to the warps first
+        TRACE(7);
+        fence_async_smem();
+        __syncthreads();
+        TRACE(8);
+        for (int e = warp + kWarps * lane; e < (nspans >> 1) * CG; e += kThreads) {
+            const int k = e / CG, ch = e - k * CG;
+            const BandSpan sp = band_span(pl, rowtab, t0, H, 2 * k + 1);
+            if (sp.nrows > 0)
+                bulk_s2g(gxb + (size_t)ch * fpx + (size_t)sp.row * W, tile + ch * tile_plane + sp.slot * W,
+                         (uint32_t)(sp.nrows * W * 4));
+        }
+        // (6) the all-zero frame rows this band owns, from the zero plane.  After the tile rows by default: gx is bound by the
+        //     DRAM write rate, and taps requested behind a burst of bulk stores wait for the whole burst to drain
+        if (!(p.band_flags & 1)) zero_spans();
+        bulk_commit();
+        pending = true;
+        a = pl.b;
+        TRACE(9);
+    }
+    {   // this CTA's share of the all-zero rows above and below the crop
+        int ra, na, rb, nb;
+        band_edge_rows(sm.flags[0], sm.flags[1], H, rank, cs, ra, na, rb, nb);
+        const int ca = (na + zrows - 1) / zrows, cb = (nb + zrows - 1) / zrows;
+        for (int e = warp + kWarps * lane; e < (ca + cb) * CG; e += kThreads) {
+            const int k = e / CG, ch = e - k * CG;
+            const int row = k < ca ? ra + k * zrows : rb + (k - ca) * zrows;
+            const int nr = k < ca ? min(zrows, na - k * zrows) : min(zrows, nb - (k - ca) * zrows);
+            bulk_s2g(gxb + (size_t)ch * fpx + (size_t)row * W, zero_plane, (uint32_t)(nr * W * 4));
+        }
+        bulk_commit();
+    }
+    reduce_gtheta(p, s, sm, n, rank, cs);
+    TRACE(10);
+    bulk_wait_read();
+    TRACE(11);
+#ifdef STN_BAND_TRACE
+    if (threadIdx.x == 0 && g_band_trace) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_band_trace[(size_t)blockIdx.x * 16 + 15] = smid;
+    }
+#endif                                                 // shared memory stays valid until the TMA unit has read it
+}
+
+// ------------------------------------------------------------------------------------------ host launcher
+// tuning knobs (loans_stn_configure): 0 = automatic
+static int g_band_cs = 0, g_band_rows = 0, g_band_tile_kb = 0, g_band_variant = 0;
+void band_tuning(int which, int value)
+{
+    if (which == 0) g_band_cs = value;
+    else if (which == 1) g_band_rows = value;
+    else if (which == 2) g_band_tile_kb = value;
+    else g_band_variant = value;
+}
+
+template <typename GT, int CG, int ILP, int MINB>
+static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+{
+    if (smem > 48 * 1024) {
+        static size_t granted = 0;
+        if (smem > granted) {
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            granted = smem;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB>, p);
+}
+
+template <typename GT, int CG>
+static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+{
+    switch (g_band_variant & 15) {
+    case 1: return launch_band_ttt<GT, CG, 1, 4>(p, ctas, cs, smem, s);
+    case 2: return launch_band_ttt<GT, CG, 2, 4>(p, ctas, cs, smem, s);
+    default: return launch_band_ttt<GT, CG, 2, 3>(p, ctas, cs, smem, s);
+    }
+}
+
+// Returns -1 when the shape is not one the band kernel takes (the caller then launches the general kernel).
+int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream)
+{
+    if (!p.gx || p.K != 1 || p.mask01 != 0.0f) return -1;
+    if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
+    if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.gx) & 15) != 0) return -1;
+    if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
+    if ((long long)p.H * p.W * p.C > 0x7fffffffLL) return -1;
+    const size_t slot_bytes = sizeof(float) * (size_t)p.W * p.C;
+    // shared memory: tile + zero plane within ~53 KB, so that four CTAs fit an SM next to their tables
+    const size_t budget = (size_t)(g_band_tile_kb > 0 ? g_band_tile_kb : 53) * 1024;
+    int zrows = (int)(2048 / (sizeof(float) * p.W));
+    if (zrows < 1) zrows = 1;
+    p.band_zero_bytes = (int)(sizeof(float) * p.W * zrows);
+    if (budget < (size_t)p.band_zero_bytes + 4 * slot_bytes) return -1;   // frame rows too wide for the tile
+    const int cap_max = (int)((budget - p.band_zero_bytes) / slot_bytes);
+    // CTAs per crop (= cluster size): 8 while that leaves every CTA at least one crop row
+    unsigned cs = g_band_cs > 0 ? (unsigned)g_band_cs : 8;
+    while (cs > 1 && (int)cs > p.oH) cs >>= 1;
+    p.ctas_per_crop = (int)cs;
+    p.px_per_cta = (int)(((long long)p.oH * p.oW + cs - 1) / cs);     // declined crops: theta role share
+    p.band_rows_cta = (p.oH + (int)cs - 1) / (int)cs;
+    // crop rows per band: a band of r rows needs 2r tile rows when the crop steps by >= ~2 frame rows (compact tile), and up
+    // to ceil(2.2 (r - 1)) + 3 when it steps by less (dense tile, stn_band_plan.cuh); bands of a CTA evenly sized
+    int max_r = 1;
+    while (max_r < p.band_rows_cta && (22 * max_r + 9) / 10 + 3 <= cap_max && 2 * (max_r + 1) <= cap_max) ++max_r;
+    const int nb = (p.band_rows_cta + max_r - 1) / max_r;
+    p.band_rows = (p.band_rows_cta + nb - 1) / nb;
+    if (g_band_rows > 0 && g_band_rows < p.band_rows) p.band_rows = g_band_rows;
+    {
+        const int need = (22 * (p.band_rows - 1) + 9) / 10 + 3 > 2 * p.band_rows ? (22 * (p.band_rows - 1) + 9) / 10 + 3 : 2 * p.band_rows;
+        p.band_cap = need < cap_max ? need : cap_max;
+    }
+    p.band_flags = g_band_variant >> 4;
+    p.band_tab_rows = p.band_rows_cta + kBandMaxHalo + 1;
+    p.band_tile_bytes = (int)(slot_bytes * p.band_cap);
+    // declined crops run the general gx role with vector stores: same tile geometry as launch_crop_bwd
+    {
+        const int nx = (p.W + 63) / 64;
+        const int tw = (((p.W + nx - 1) / nx) + 3) & ~3;
+        const int tr = p.H < 8 ? p.H : 8;
+        p.gx_tile_rows = tr; p.gx_tile_cols = tw; p.gx_tile_pitch = tw;
+        p.gx_tiles_x = (p.W + tw - 1) / tw;
+        p.gx_tiles_per_frame = p.gx_tiles_x * ((p.H + tr - 1) / tr);
+        p.gx_tile_bytes = (int)(sizeof(float) * (size_t)p.C * tr * tw * kWarps);
+        p.gx_vec4 = 1; p.gx_tma_store = 0; p.gx_zero_bytes = 0;
+        p.band_fb_tiles_per_warp = (p.gx_tiles_per_frame + kWarps * (int)cs - 1) / (kWarps * (int)cs);
+    }
+    const int region = p.band_tile_bytes + p.band_zero_bytes;
+    p.band_region_bytes = ((region > p.gx_tile_bytes ? region : p.gx_tile_bytes) + 127) & ~127;
+    const size_t smem = (size_t)p.band_region_bytes + sizeof(BwdSmem) + sizeof(BandAxis) * (size_t)(p.oW + p.band_tab_rows) +
+                        sizeof(int2) * (size_t)p.band_tab_rows + sizeof(float) * (size_t)((p.oW + p.oH + 3) & ~3) + sizeof(ScatterGeom);
+    if (smem > 200 * 1024) return -1;
+    const long long ctas = (long long)p.N * cs;
+    if (ctas > 0x7fffffffLL) return -1;
+    cudaError_t e;
+    if (gy_dtype == 0)
+        e = p.C == 1 ? launch_band_tt<float, 1>(p, (unsigned)ctas, cs, smem, stream)
+          : p.C == 3 ? launch_band_tt<float, 3>(p, (unsigned)ctas, cs, smem, stream)
+                     : launch_band_tt<float, 4>(p, (unsigned)ctas, cs, smem, stream);
+    else
+        e = p.C == 1 ? launch_band_tt<__nv_bfloat16, 1>(p, (unsigned)ctas, cs, smem, stream)
+          : p.C == 3 ? launch_band_tt<__nv_bfloat16, 3>(p, (unsigned)ctas, cs, smem, stream)
+                     : launch_band_tt<__nv_bfloat16, 4>(p, (unsigned)ctas, cs, smem, stream);
+    count_launch();
+    if (e != cudaSuccess) return set_error("crop_bwd (band) launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+#ifdef STN_BAND_TRACE
+extern "C" int loans_stn_debug_band_trace(void *buf)
+{
+    long long *q = reinterpret_cast<long long *>(buf);
+    return cudaMemcpyToSymbol(g_band_trace, &q, sizeof(q)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+}  // namespace stn

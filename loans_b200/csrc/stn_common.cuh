@@ -37,6 +37,12 @@ struct CropParams {
     int gx_zero_bytes;       // one zero plane per CTA behind the tiles: source of the stores of untouched tiles
     // separable path (stn_separable.cu)
     int sep_rows, sep_pitch, sep_buf_offset, gx_tiles_per_warp;
+    // band backward (stn_band.cu): ctas_per_crop CTAs (one cluster) per crop, band_rows_cta crop rows each, worked
+    // through in bands of at most band_rows crop rows; the tile holds band_cap frame rows of W floats per channel
+    int band_rows_cta, band_rows, band_cap, band_tab_rows;
+    int band_tile_bytes, band_zero_bytes, band_region_bytes;   // region = tile + zero plane, or the general roles' warp tiles
+    int band_flags;                                             // A/B switches (bit 0: zero rows stored early, bit 1: no L2 prefetch of the taps)
+    int band_fb_tiles_per_warp;                                 // declined crops: tiles per warp in the general gx role
 };
 
 template <typename T> struct Elem;

@@ -41,6 +41,44 @@ struct BwdSmem {
     int flags[2];
 };
 
+// The six per-thread partial sums of gtheta -> gtheta[n]: warp shuffles, shared memory, then cluster rank 0 adds the
+// per-CTA partials through distributed shared memory in rank order (deterministic, no atomics, no workspace).
+// Every CTA of the cluster must call it.
+__device__ __forceinline__ void reduce_gtheta(const CropParams &p, const float (&s)[6], BwdSmem &sm, int n, int rank, int cs)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float r = warp_sum(s[k]);
+        if (lane == 0) sm.red[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float tot = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
+        sm.part[threadIdx.x] = tot;
+    }
+    float *out = p.gtheta + 6 * (size_t)n;
+    if (cs > 1) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        cl.sync();                                         // every CTA's part[] is written and visible
+        if (rank == 0 && threadIdx.x < 6) {
+            float tot = 0.f;
+            for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
+            // backward of the rotation mask: [0,1] and [1,0] are scaled (functions/rotation_droput.py:48)
+            if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
+            out[threadIdx.x] = tot;
+        }
+        cl.sync();                                         // peers keep their shared memory until rank 0 has read it
+    } else if (threadIdx.x < 6) {
+        float tot = sm.part[threadIdx.x];
+        if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
+        out[threadIdx.x] = tot;
+    }
+
+}
+
 template <typename GT, int CG, bool EXACT>
 __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
 {
@@ -162,36 +200,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
         s[3] = fmaf(sv, xsj, s[3]); s[4] = fmaf(sv, ysi, s[4]); s[5] += sv;
     }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const float r = warp_sum(s[k]);
-        if (lane == 0) sm.red[warp][k] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        float tot = 0.f;
-#pragma unroll
-        for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
-        sm.part[threadIdx.x] = tot;
-    }
-    float *out = p.gtheta + 6 * (size_t)n;
-    if (cs > 1) {
-        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-        cl.sync();                                         // every CTA's part[] is written and visible
-        if (rank == 0 && threadIdx.x < 6) {
-            float tot = 0.f;
-            for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
-            // backward of the rotation mask: [0,1] and [1,0] are scaled (functions/rotation_droput.py:48)
-            if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-            out[threadIdx.x] = tot;
-        }
-        cl.sync();                                         // peers keep their shared memory until rank 0 has read it
-    } else if (threadIdx.x < 6) {
-        float tot = sm.part[threadIdx.x];
-        if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
-        out[threadIdx.x] = tot;
-    }
+    reduce_gtheta(p, s, sm, n, rank, cs);
 }
 
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../loans_b200/csrc/stn_math.cuh"
+#include "../../loans_b200/csrc/stn_band_plan.cuh"
 
 using namespace stn;
 
@@ -190,6 +191,135 @@ long long emu_gx_scatter(const float *theta, float mask01, const float *gy, floa
                                 gx[((size_t)f * c + c0 + ch) * plane + (size_t)(r0 + row) * w + s0 + col] = acc[ch];
                         }
             }
+    }
+    return conflicts;
+}
+
+// The band backward (stn_band.cu) exactly as its CTAs run it -- same planning code (stn_band_plan.cuh), same
+// per-pixel arithmetic -- executed serially: `cs` CTAs per crop, `cap` tile rows.  Checks what cannot be seen from
+// the result alone: returns the number of tile addresses two crop pixels of the SAME phase wrote (a race on the
+// GPU); stats[0] = gx elements of band-path frames not written exactly once, stats[1] = largest phase count,
+// stats[2] = bands, stats[3] = tile slots out of range.  ok[n] = 1 where the band path takes the crop; the other
+// frames / crops are left untouched (the kernel sends them to the general roles).
+long long emu_band_bwd(const float *x, const float *theta, float mask01, const float *gy, const float *ggrid_up,
+                       float *gtheta, float *gx, float *ggrid_out, int *ok,
+                       int n, int c, int h, int w, int oh, int ow, int cs, int cap, int max_rows, long long *stats)
+{
+    const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
+    const int npx = oh * ow;
+    const size_t plane = (size_t)h * w;
+    long long conflicts = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    std::vector<BandAxis> coltab(ow), rowtab(oh + 1);
+    std::vector<float> tile((size_t)c * cap * w);
+    std::vector<int> stamp((size_t)c * cap * w);
+    std::vector<int> written(plane * c);
+    int phase_id = 0;
+    for (int b = 0; b < n; ++b) {
+        const Theta th = load_theta_masked(theta + 6 * b, mask01);
+        const BandCrop bc = make_band_crop(th, h, w, oh, ow);
+        ok[b] = bc.ok;
+        if (!bc.ok) continue;
+        if (bc.P * bc.Q > stats[1]) stats[1] = bc.P * bc.Q;
+        const float *xb = x + (size_t)b * c * plane;
+        const float *gyb = gy + (size_t)b * c * npx;
+        float *gxb = gx + (size_t)b * c * plane;
+        std::fill(written.begin(), written.end(), 0);
+        for (int j = 0; j < ow; ++j) coltab[j] = make_band_axis(th.t00, th.t01, th.t02, linspace_pm1(j, ow, xstep), true, w);
+        float s[6] = {0, 0, 0, 0, 0, 0};
+        const int rows_cta = (oh + cs - 1) / cs;
+        int L, E, tmp;
+        band_row_range(make_band_axis(th.t11, th.t10, th.t12, linspace_pm1(0, oh, ystep), false, h), h, L, tmp);
+        band_row_range(make_band_axis(th.t11, th.t10, th.t12, linspace_pm1(oh - 1, oh, ystep), false, h), h, tmp, E);
+        for (int rank = 0; rank < cs; ++rank) {
+            const int i0 = rank * rows_cta, i1 = i0 + rows_cta < oh ? i0 + rows_cta : oh;
+            {   // this CTA's share of the all-zero rows above and below the crop
+                int ra, na, rb, nb;
+                band_edge_rows(L, E, h, rank, cs, ra, na, rb, nb);
+                for (int ch = 0; ch < c; ++ch)
+                    for (int part = 0; part < 2; ++part)
+                        for (int r = 0; r < (part ? nb : na); ++r)
+                            for (int col = 0; col < w; ++col) {
+                                const size_t o = (size_t)ch * plane + (size_t)((part ? rb : ra) + r) * w + col;
+                                gxb[o] = 0.0f;
+                                written[o]++;
+                            }
+            }
+            if (i0 >= i1) continue;
+            const int t0 = i0 - (bc.P - 1) < 0 ? 0 : i0 - (bc.P - 1), t1 = i1 + 1 < oh ? i1 + 1 : oh;
+            for (int i = t0; i < t1; ++i)
+                rowtab[i - t0] = make_band_axis(th.t11, th.t10, th.t12, linspace_pm1(i, oh, ystep), false, h);
+            for (int a = i0; a < i1;) {
+                const BandPlan pl = plan_band(rowtab.data(), t0, a, i1, oh, h, bc.P, cap, max_rows, E);
+                stats[2]++;
+                if (pl.nslots > cap || pl.b <= a) { stats[3]++; return -1; }
+                std::fill(tile.begin(), tile.end(), 0.f);
+                std::fill(stamp.begin(), stamp.end(), -1);
+                const int tile_plane = cap * w;
+                for (int ph = 0; ph < bc.P * bc.Q; ++ph) {
+                    ++phase_id;
+                    for (int i = pl.h; i < pl.b; ++i)
+                        for (int j = 0; j < ow; ++j) {
+                            if ((i % bc.P) * bc.Q + (j % bc.Q) != ph) continue;
+                            const BandAxis &col = coltab[j], &row = rowtab[i - t0];
+                            const Tap t = tap_from_band_axes(col, row, h, w);
+                            const TapAddr ad = make_tap_addr(t, h, w);
+                            int s0, s1;
+                            band_row_slots(pl, row, i, s0, s1);
+                            if (s0 >= cap || s1 >= cap) { stats[3]++; return -1; }
+                            float su = 0, sv = 0;
+                            for (int ch = 0; ch < c; ++ch) {
+                                float x1, x2, x3, x4, gu, gv;
+                                load_taps(xb + ch * plane, ad, w, x1, x2, x3, x4);
+                                const float g = gyb[(size_t)ch * npx + (size_t)i * ow + j];
+                                grad_uv(t, x1, x2, x3, x4, gu, gv);
+                                gu = f_mul(gu, g); gv = f_mul(gv, g);
+                                if (ch == 0) { su = gu; sv = gv; } else { su = f_add(su, gu); sv = f_add(sv, gv); }
+                                const float a1 = f_mul(g, t.wu1), a0 = f_mul(g, t.wu0);
+                                const int cix = t.u0 - 1;
+                                const int adr[4] = {s0 * w + cix, s0 * w + cix + 1, s1 * w + cix, s1 * w + cix + 1};
+                                const bool okt[4] = {s0 >= 0 && (col.code & kAxTap0), s0 >= 0 && (col.code & kAxTap1),
+                                                     s1 >= 0 && (col.code & kAxTap0), s1 >= 0 && (col.code & kAxTap1)};
+                                const float val[4] = {f_mul(a1, t.wv1), f_mul(a0, t.wv1), f_mul(a1, t.wv0), f_mul(a0, t.wv0)};
+                                for (int t4 = 0; t4 < 4; ++t4)
+                                    if (okt[t4]) {
+                                        const int o = ch * tile_plane + adr[t4];
+                                        if (stamp[o] == phase_id) ++conflicts;
+                                        stamp[o] = phase_id;
+                                        tile[o] = f_add(tile[o], val[t4]);
+                                    }
+                            }
+                            if (i < pl.a) continue;                 // halo row: scatter only
+                            finish_grad_uv(t, h, w, su, sv);
+                            const size_t q = (size_t)i * ow + j;
+                            if (ggrid_out) { ggrid_out[(size_t)b * 2 * npx + q] = su; ggrid_out[(size_t)b * 2 * npx + npx + q] = sv; }
+                            if (ggrid_up) {
+                                su = f_add(su, ggrid_up[(size_t)b * 2 * npx + q]);
+                                sv = f_add(sv, ggrid_up[(size_t)b * 2 * npx + npx + q]);
+                            }
+                            s[0] += su * col.lin; s[1] += su * row.lin; s[2] += su;
+                            s[3] += sv * col.lin; s[4] += sv * row.lin; s[5] += sv;
+                        }
+                }
+                const int ns = band_span_count(pl);
+                for (int t = 0; t < ns; ++t) {
+                    const BandSpan sp = band_span(pl, rowtab.data(), t0, h, t);
+                    if (sp.nrows <= 0) continue;
+                    if (sp.slot >= 0 && sp.slot + sp.nrows > cap) { stats[3]++; return -1; }
+                    for (int ch = 0; ch < c; ++ch)
+                        for (int r = 0; r < sp.nrows; ++r)
+                            for (int col = 0; col < w; ++col) {
+                                const size_t o = (size_t)ch * plane + (size_t)(sp.row + r) * w + col;
+                                gxb[o] = sp.slot >= 0 ? tile[(size_t)ch * tile_plane + (size_t)(sp.slot + r) * w + col] : 0.0f;
+                                written[o]++;
+                            }
+                }
+                a = pl.b;
+            }
+        }
+        for (size_t o = 0; o < plane * c; ++o) stats[0] += written[o] != 1;
+        s[1] = f_mul(s[1], mask01); s[3] = f_mul(s[3], mask01);
+        for (int e = 0; e < 6; ++e) gtheta[6 * b + e] = s[e];
     }
     return conflicts;
 }

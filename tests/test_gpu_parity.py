@@ -241,3 +241,80 @@ def test_axis_aligned_kernels_on_ragged_shapes(G, shape):
         _full_check(G, x, theta, (oh, ow), 0.0, 1, seed=7)
     finally:
         _lib.tma_forward(False)
+
+
+# ------------------------------------------------------------------------------------------------ band backward
+BAND_THETAS = np.array([
+    [[1, 0, 0], [0, 1, 0]], [[0.8, 0, 0], [0, 0.8, 0]], [[0.6, 0, 0.3], [0, 0.7, -0.25]], [[0.9, 0, 0.8], [0, 0.9, -0.7]],
+    [[0.5, 0, 7.0], [0, 0.5, -9.0]], [[0.5, 0, 0.0], [0, 0.5, -1.6]], [[1.7, 0, 0.1], [0, 2.5, -0.2]],
+    [[40.0, 0, 0.5], [0, 55.0, 0.1]], [[0.9, 0, 0.0], [0, 0.15, 0.1]], [[0.2, 0, 0.3], [0, 0.25, -0.2]],
+    [[0.05, 0, 0.3], [0, 0.06, -0.2]], [[-0.8, 0, 0.1], [0, 0.7, 0]], [[0, 0, 0.2], [0, 0.8, 0]],
+    [[0.7, 0.4, 0], [-0.3, 0.6, 0.1]], [[0.3, 0, -0.5], [0, 0.33, 0.4]], [[0.55, 0, 0.05], [0, 0.52, 0.0]],
+], np.float32)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(3, 24, 24, 9, 9), (3, 17, 32, 12, 7), (1, 8, 8, 16, 16), (3, 20, 12, 1, 5),
+                                   (4, 13, 8, 6, 1), (3, 64, 48, 5, 33), (3, 40, 40, 37, 3), (3, 96, 128, 75, 75)])
+def test_band_backward_hard_boxes(G, shape, variant):
+    """The band kernel (mask01 == 0, one crop per frame) on boxes that exercise every branch of its plan: compact and
+    dense tiles, halos, clipped rows, crops it declines (mirrored, 20x up-sampling, zero scale) -- against the oracle."""
+    from loans_b200 import _lib
+    c, h, w, oh, ow = shape
+    rng = np.random.default_rng(sum(shape))
+    x = rng.random((len(BAND_THETAS), c, h, w), dtype=np.float32)
+    try:
+        _lib.band_backward(True)
+        n0 = _lib.launch_count()
+        for cs, rows in ((0, 0), (1, 1), (2, 3), (4, 0)):
+            _lib.band_tuning(cs=cs, rows=rows, variant=variant)
+            _full_check(G, x, BAND_THETAS, (oh, ow), 0.0, 1, seed=11)
+        assert _lib.launch_count() - n0 == 8            # one forward + one backward launch per check
+    finally:
+        _lib.band_tuning()
+        _lib.band_backward(None)
+
+
+@pytest.mark.parametrize("name,batch", [("cfg1", None), ("cfg2", 16), ("cfg3", 6), ("cfg5", 24)])
+def test_band_backward_matches_the_general_kernel(G, name, batch):
+    from loans_b200 import _lib
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True, with_ggrid=True)
+    d["theta"][::5, :, 2] += 0.9                      # some crops hanging out of the frame
+    d["theta"][1::7, 0, 0] *= -1.0                    # mirrored crops: declined, general roles inside the band launch
+    d["theta"][2::9, :, :2] *= 0.2                    # up-sampling crops: phased, dense tiles
+    osz = (wl.out_h, wl.out_w)
+    try:
+        _lib.band_backward(True)
+        n0 = _lib.launch_count()
+        b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+        assert _lib.launch_count() - n0 == 1
+        b2 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+        _lib.band_backward(False)
+        b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+    finally:
+        _lib.band_backward(None)
+    assert np.array_equal(b0[2], b1[2])                                   # ggrid bit-exact
+    assert G.rel_max(b1[1], b0[1]) <= 2e-6 and G.rel_max(b1[0], b0[0]) <= 1e-5
+    assert np.array_equal(b1[0], b2[0]) and np.array_equal(b1[1], b2[1])   # bit-reproducible
+    gt0, gx0, gg0 = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+    assert np.array_equal(b1[2], gg0)
+    assert G.rel_max(b1[1], gx0) <= 2e-6 and G.rel_max(b1[0], gt0) <= GRAD_TOL
+
+
+def test_band_backward_full_size_adjoint(G):
+    from loans_b200 import _lib
+    wl = W.WORKLOADS["cfg2"]
+    d = W.make_inputs(wl, rotate=False)
+    osz = (wl.out_h, wl.out_w)
+    y, _ = G.crop_fwd(d["x"], d["theta"], osz, 0.0, 1, want_grid=False)
+    try:
+        _lib.band_backward(True)
+        gt, gx, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], None, 0.0, 1, want_ggrid=False)
+    finally:
+        _lib.band_backward(None)
+    lhs = float((y.astype(np.float64) * d["gy"]).sum())
+    rhs = float((d["x"].astype(np.float64) * gx).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-3, (lhs, rhs)
+    gt0, gx0, _ = oc.crop_backward(d["x"][:4], d["theta"][:4], osz, d["gy"][:4], None, 0.0, 1)
+    assert G.rel_max(gx[:4], gx0) <= 2e-6 and G.rel_max(gt[:4], gt0) <= GRAD_TOL

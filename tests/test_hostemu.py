@@ -156,3 +156,115 @@ def test_golden_fixture(emu):
         assert np.array_equal(y, g[p + "y"]) and np.array_equal(grid, g[p + "grid"]) and np.array_equal(ggo, g[p + "ggrid"])
         assert np.abs(gx - g[p + "gx"]).max() <= 2e-6 * max(1.0, np.abs(g[p + "gx"]).max())
         assert np.abs(gt - g[p + "gtheta"]).max() <= 1e-4 * max(1.0, np.abs(g[p + "gtheta"]).max())
+
+
+# ------------------------------------------------------------------------------------------------ band backward
+def run_band(lib, x, theta, osz, gy, gg, mask, cs, cap, max_rows=1 << 20):
+    b, c, h, w = x.shape
+    n = theta.shape[0]
+    oh, ow = osz
+    lib.emu_band_bwd.argtypes = [_f, _f, ctypes.c_float, _f, _f, _f, _f, _f, ctypes.POINTER(ctypes.c_int)] + \
+        [ctypes.c_int] * 9 + [ctypes.POINTER(ctypes.c_longlong)]
+    lib.emu_band_bwd.restype = ctypes.c_longlong
+    gt = np.full((n, 2, 3), np.nan, np.float32)
+    gx = np.full_like(x, np.nan)
+    ggo = np.full((n, 2, oh, ow), np.nan, np.float32)
+    ok = np.zeros(n, np.int32)
+    stats = (ctypes.c_longlong * 4)()
+    conflicts = lib.emu_band_bwd(_p(x), _p(theta), mask, _p(gy), _p(gg), _p(gt), _p(gx), _p(ggo),
+                                 ok.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n, c, h, w, oh, ow, cs, cap, max_rows, stats)
+    return gt, gx, ggo, ok.astype(bool), conflicts, list(stats)
+
+
+def check_band(lib, x, theta, osz, mask=0.0, seed=0, expect_ok=None, layouts=((1, 4), (2, 6, 2), (3, 16), (8, 19), (5, 7, 1))):
+    rng = np.random.default_rng(seed)
+    n, c = theta.shape[0], x.shape[1]
+    gy = rng.standard_normal((n, c) + tuple(osz), dtype=np.float32)
+    gg = rng.standard_normal((n, 2) + tuple(osz), dtype=np.float32)
+    gt0, gx0, gg0 = oc.crop_backward(x, theta, osz, gy, gg, mask, 1)
+    oks = None
+    for lay in layouts:
+        cs, cap = lay[:2]
+        max_rows = lay[2] if len(lay) > 2 else 1 << 20
+        cs = min(cs, osz[0])
+        gt, gx, ggo, ok, conflicts, stats = run_band(lib, x, theta, osz, gy, gg, mask, cs, cap, max_rows)
+        assert conflicts == 0, ("same-phase write conflicts", conflicts, stats, cs, cap)
+        assert stats[0] == 0, ("gx elements not written exactly once", stats, cs, cap)
+        assert stats[3] == 0, ("tile slot out of range", stats, cs, cap)
+        if expect_ok is not None:
+            assert list(ok) == list(expect_ok), (ok, expect_ok)
+        if not ok.any():
+            continue
+        assert np.array_equal(ggo[ok], gg0[ok]), "ggrid not bit-exact"
+        assert not np.isnan(gx[ok]).any()
+        sc = max(1.0, float(np.abs(gx0).max()))
+        assert np.abs(gx[ok] - gx0[ok]).max() <= 2e-6 * sc, ("gx", np.abs(gx[ok] - gx0[ok]).max(), sc, cs, cap)
+        sc = max(1.0, float(np.abs(gt0).max()))
+        assert np.abs(gt[ok] - gt0[ok]).max() <= 1e-4 * sc, ("gtheta", np.abs(gt[ok] - gt0[ok]).max(), sc)
+        oks = ok
+    return oks
+
+
+@pytest.mark.parametrize("wl,batch", [("cfg2", 6), ("cfg1", 4), ("cfg3", 2), ("cfg5", 4)])
+def test_band_backward_on_workload_shapes(emu, wl, batch):
+    wl = W.WORKLOADS[wl]
+    d = W.make_inputs(wl, batch=batch, rotate=True)
+    ok = check_band(emu, d["x"], d["theta"], (wl.out_h, wl.out_w), 0.0, layouts=((8, 16), (8, 18), (4, 12), (1, 6)))
+    assert ok is not None and ok.all()            # every synthetic LoANs crop is a down-sampling, upright box
+
+
+BAND_THETAS = {
+    "identity": [[1, 0, 0], [0, 1, 0]],
+    "loans_init": [[0.8, 0, 0], [0, 0.8, 0]],
+    "shifted": [[0.6, 0, 0.3], [0, 0.7, -0.25]],
+    "half_outside": [[0.9, 0, 0.8], [0, 0.9, -0.7]],
+    "far_outside": [[0.5, 0, 7.0], [0, 0.5, -9.0]],
+    "just_outside_top": [[0.5, 0, 0.0], [0, 0.5, -1.6]],
+    "bigger_than_frame": [[1.7, 0, 0.1], [0, 2.5, -0.2]],
+    "huge_scale": [[40.0, 0, 0.5], [0, 55.0, 0.1]],
+    "anisotropic": [[0.9, 0, 0.0], [0, 0.15, 0.1]],
+    "upsample_2x": [[0.2, 0, 0.3], [0, 0.25, -0.2]],
+    "upsample_8x": [[0.05, 0, 0.3], [0, 0.06, -0.2]],
+    "edge_exact": [[1.0, 0, 2.0 / 23.0], [0, 1.0, 0]],
+    "flip_x": [[-0.8, 0, 0.1], [0, 0.7, 0]],                   # not taken by the band path
+    "zero_x_only": [[0, 0, 0.2], [0, 0.8, 0]],                 # not taken
+    "rot_masked": [[0.7, 0.4, 0], [-0.3, 0.6, 0.1]],           # rotation terms masked away by mask01 == 0
+}
+
+
+@pytest.mark.parametrize("name", sorted(BAND_THETAS))
+@pytest.mark.parametrize("shape", [(24, 24, 9, 9), (17, 32, 12, 7), (8, 8, 16, 16), (20, 12, 1, 5), (13, 8, 6, 1),
+                                   (64, 48, 5, 33), (40, 40, 37, 3)])
+def test_band_backward_hard_transforms(emu, name, shape):
+    h, w, oh, ow = shape
+    rng = np.random.default_rng(abs(hash((name, shape))) % (2 ** 31))
+    x = rng.random((1, 3, h, w), dtype=np.float32)
+    check_band(emu, x, _theta([BAND_THETAS[name]]), (oh, ow), 0.0, seed=3)
+
+
+def test_band_backward_random_boxes(emu):
+    rng = np.random.default_rng(7)
+    taken = 0
+    for it in range(120):
+        h, w = int(rng.integers(2, 48)), int(rng.integers(1, 12)) * 4
+        oh, ow = int(rng.integers(1, 28)), int(rng.integers(1, 28))
+        b = int(rng.integers(1, 3))
+        c = int(rng.integers(1, 5))
+        x = rng.random((b, c, h, w), dtype=np.float32)
+        theta = np.zeros((b, 2, 3), np.float32)
+        theta[:, 0, 0] = np.exp(rng.uniform(np.log(0.03), np.log(4.0), b))
+        theta[:, 1, 1] = np.exp(rng.uniform(np.log(0.03), np.log(4.0), b))
+        theta[:, :, 2] = rng.uniform(-1.5, 1.5, (b, 2))
+        theta[:, 0, 1] = rng.uniform(-1, 1, b)         # masked away
+        theta[:, 1, 0] = rng.uniform(-1, 1, b)
+        cs, cap, mr = int(rng.integers(1, 9)), int(rng.integers(2, 24)), int(rng.integers(1, 12))
+        ok = check_band(emu, x, theta, (oh, ow), 0.0, seed=it, layouts=((cs, cap, mr),))
+        taken += 0 if ok is None else int(ok.sum())
+    assert taken > 60
+
+
+def test_band_backward_declines_rotations(emu):
+    x = np.random.default_rng(0).random((1, 3, 16, 16), dtype=np.float32)
+    check_band(emu, x, _theta([[[0.7, 0.1, 0], [0, 0.7, 0]]]), (8, 8), 1.0, expect_ok=[False], layouts=((2, 8),))
+    check_band(emu, x, _theta([[[0.7, 0.1, 0], [0, 0.7, 0]]]), (8, 8), 0.0, expect_ok=[True], layouts=((2, 8),))
+    check_band(emu, x, _theta([[[np.nan, 0, 0], [0, 0.7, 0]]]), (8, 8), 0.0, expect_ok=[False], layouts=((2, 8),))
