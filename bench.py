@@ -43,6 +43,9 @@ def parse_args():
                          "or a number used as the test-mode mask value")
     ap.add_argument("--no-variants", action="store_true", help="skip the second (general-affine / as-shipped) timing")
     ap.add_argument("--tma-forward", action="store_true", help="opt into the TMA-staged forward kernel (axis-aligned crops)")
+    ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch (A/B)")
+    ap.add_argument("--band", default="auto", choices=["auto", "on", "off"], help="band backward kernel: library default / always / never")
+    ap.add_argument("--no-cudnn", action="store_true", help="skip the cuDNN comparison arm (the reference's GPU path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per worker for the cpu_baseline leg")
@@ -247,6 +250,10 @@ def run_ours(args):
     L = _lib.lib()
     if args.tma_forward:
         _lib.tma_forward(True)
+    if args.no_pdl:
+        _lib.pdl(False)
+    if args.band != "auto":
+        _lib.band_backward(args.band == "on")
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -369,6 +376,26 @@ def run_ours(args):
             "fwd_us": ms_af * 1e3, "bwd_us": ms_ab * 1e3,
             "whole_step_frac": (fwd_bytes + bwd_bytes) / (ms_a * 1e-3) / 1e9}
 
+    # ---- the reference's GPU path on the same inputs: cuDNN's spatial-transformer kernels (what chainer calls on a GPU)
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cudnn and K == 1 and not bf16 and need_gx:
+        try:
+            from baseline.cudnn_stn import time_cudnn
+            us_c, ver, (y_c, gx_c, gt_c) = time_cudnn(wl, sets, float(mask01), max(1, steps // S), dev)
+            fwd(sets[0]); bwd(sets[0])
+            torch.cuda.synchronize()
+
+            def rel(a, b):
+                return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+            gpu_ref = {"impl": "cuDNN %d cudnnSpatialTfGridGenerator/Sampler Forward+Backward + chainer's grid layout copy "
+                               "(the kernels chainer 4.1.0 runs for this path on a GPU), same inputs, CUDA-graph replay" % ver,
+                       "us_per_step": us_c, "value": N / (us_c * 1e-6), "unit": UNIT,
+                       "ours_vs_cudnn_speedup": us_c / (ms_step * 1e3),
+                       "max_rel_diff_vs_ours": {"y": rel(sets[0]["y"].float(), y_c), "gx": rel(sets[0]["gx"], gx_c),
+                                                "gtheta": rel(sets[0]["gtheta"], gt_c)}}
+        except Exception as e:            # comparison arm only: report why it is missing
+            gpu_ref = {"unavailable": repr(e)[:300]}
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
@@ -381,7 +408,7 @@ def run_ours(args):
     ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9
     ach_f = fwd_bytes / (ms_f * 1e-3) / 1e9
     ach_s = (fwd_bytes + bwd_bytes) / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "backward launch (gx role + cluster-reduced theta role): stn_sep_bwd_kernel when mask01 == 0, else stn_bwd_kernel",
+    roofline = {"bound": "hbm", "kernel": "backward launch: stn_bwd_kernel (gx role + cluster-reduced theta role), or stn_bwd_band_kernel where the band backward is taken (mask01 == 0, wide frame rows)",
                 "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_us": ms_b * 1e3,
                 "fwd_kernel": {"achieved": ach_f, "frac": ach_f / peak, "algorithmic_bytes_per_launch": fwd_bytes,
@@ -468,9 +495,11 @@ def run_ours(args):
                 "config": workload_config(wl, need_gx, {
                     "l2": "rotating %d distinct input/output sets (%.0f MB each, %.0f MB total > 126 MB L2)"
                           % (S, set_bytes / 1e6, S * set_bytes / 1e6),
-                    "launch": "CUDA-graph replay of the C-ABI calls loans_stn_crop_fwd + loans_stn_crop_bwd"}),
+                    "launch": "CUDA-graph replay of the C-ABI calls loans_stn_crop_fwd + loans_stn_crop_bwd, "
+                              + ("plain launches" if args.no_pdl else "programmatic dependent launch (griddepcontrol) between consecutive kernels"),
+                    "band_backward": args.band}),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
-                "roofline": roofline, "cpu_baseline": cpu, "variants": variants}
+                "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "variants": variants}
         for v in variants.values():
             v["whole_step_frac"] = v["whole_step_frac"] / peak
         print(json.dumps(line), flush=True)

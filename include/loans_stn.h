@@ -58,7 +58,11 @@ unsigned long long loans_stn_launch_count(void);
  *   frames), 1: whenever it applies, 0: never.  gx, ggrid: same values; gtheta: same sums in a different order (both
  *   within the 1e-4 bar).
  * LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: tuning knobs of the band kernel for A/B measurements
- *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant); 0 = automatic. */
+ *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant); 0 = automatic.
+ * LOANS_STN_CFG_PDL (default 1): the fused kernels (crop_fwd, crop_bwd, sampler_fwd) are launched with programmatic
+ *   stream serialisation: their CTAs may become resident, and fill their shared-memory tables, while the previous kernel of
+ *   the stream is still draining; they touch global memory only after griddepcontrol.wait, so stream order is preserved
+ *   whatever the neighbouring kernels are.  0: plain launches. */
 #define LOANS_STN_CFG_FORCE_GENERAL 1
 #define LOANS_STN_CFG_TMA_FORWARD 2
 #define LOANS_STN_CFG_BAND_BACKWARD 3
@@ -66,6 +70,7 @@ unsigned long long loans_stn_launch_count(void);
 #define LOANS_STN_CFG_BAND_ROWS 5
 #define LOANS_STN_CFG_BAND_TILE_KB 6
 #define LOANS_STN_CFG_BAND_VARIANT 7
+#define LOANS_STN_CFG_PDL 8
 int loans_stn_configure(int key, int value);
 
 /* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.

@@ -13,6 +13,7 @@ F32, BF16 = 0, 1
 CFG_FORCE_GENERAL = 1
 CFG_TMA_FORWARD = 2
 CFG_BAND_BACKWARD = 3
+CFG_PDL = 8
 CFG_BAND_CS, CFG_BAND_ROWS, CFG_BAND_TILE_KB, CFG_BAND_VARIANT = 4, 5, 6, 7
 
 _lib = None
@@ -74,6 +75,11 @@ def force_general(on):
 def tma_forward(on):
     """Opt into the TMA-staged forward kernel for axis-aligned crops (mask01 == 0)."""
     check(lib().loans_stn_configure(CFG_TMA_FORWARD, int(bool(on))), "loans_stn_configure")
+
+
+def pdl(on):
+    """Programmatic dependent launch of the fused kernels (default on)."""
+    check(lib().loans_stn_configure(CFG_PDL, int(bool(on))), "loans_stn_configure")
 
 
 def band_backward(on):

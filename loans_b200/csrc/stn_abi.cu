@@ -42,6 +42,8 @@ void band_tuning(int which, int value);      // -1: shape not supported, use the
 
 static std::atomic<int> g_force_general{0};
 static std::atomic<int> g_tma_forward{0};
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load() != 0; }
 static std::atomic<int> g_band_backward{-1};    // -1: by shape (wide frame rows), 0: never, 1: whenever it applies
 
 static int need_device(const char *what)
@@ -102,6 +104,7 @@ int loans_stn_configure(int key, int value)
 {
     if (key == LOANS_STN_CFG_FORCE_GENERAL) { g_force_general.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_TMA_FORWARD) { g_tma_forward.store(value != 0); return 0; }
+    if (key == LOANS_STN_CFG_PDL) { g_pdl.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_BAND_BACKWARD) { g_band_backward.store(value < 0 ? -1 : (value != 0)); return 0; }
     if (key >= LOANS_STN_CFG_BAND_CS && key <= LOANS_STN_CFG_BAND_VARIANT) {
         if (value < 0) return set_error("loans_stn_configure: key %d needs a value >= 0", key);

@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
 
     TRACE(0);
+    pdl_launch_dependents();
+    {   // the zero plane needs no input: filled while the previous kernel of the stream drains
+        float4 *z4 = reinterpret_cast<float4 *>(zero_plane);
+        for (int e = threadIdx.x; e < p.band_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_async_smem();
+    }
+    pdl_wait();
     const int cs = p.ctas_per_crop;
     const int n = blockIdx.x / cs, rank = blockIdx.x - n * cs;
     const int tid = threadIdx.x;
@@ -130,11 +137,6 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         int lo, hi;
         band_row_range(make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, last ? oH - 1 : 0), false, H), H, lo, hi);
         sm.flags[last] = last ? hi : lo;
-    }
-    {
-        float4 *z4 = reinterpret_cast<float4 *>(zero_plane);
-        for (int e = tid; e < p.band_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fence_async_smem();
     }
     __syncthreads();
     TRACE(2);
@@ -377,13 +379,9 @@ static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = fill_launch_attrs(attr, cs);
     return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB>, p);
 }
 

@@ -86,9 +86,36 @@ __device__ __forceinline__ void fill_axis_tables(const CropParams &p, float *xs,
     }
 }
 
+// ---- programmatic dependent launch (PDL).  The fused kernels are launched with cudaLaunchAttributeProgrammaticStream-
+// Serialization: their CTAs may become resident, and run the part of their prologue that touches no global memory, while
+// the previous kernel of the stream is still draining.  pdl_launch_dependents() at entry lets the NEXT kernel do the
+// same; pdl_wait() returns once every prerequisite grid has completed and its memory is visible -- it comes before the
+// first global access, reads and writes alike.  Both are no-ops for a launch without programmatic edges.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- host-side error plumbing (definitions in stn_abi.cu)
 int set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);
+bool pdl_enabled();
+// fills the launch attributes shared by the fused kernels: [cluster dimension,] programmatic stream serialisation
+inline unsigned fill_launch_attrs(cudaLaunchAttribute *attr, unsigned cluster)
+{
+    unsigned na = 0;
+    if (cluster > 0) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    return na;
+}
 
 }  // namespace stn

@@ -41,10 +41,12 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
     const int C = EXACT ? CG : p.C;          // EXACT: one channel group covers all channels, loops fold away
     extern __shared__ float smem[];
     float *xs = smem, *ys = smem + p.oW;
+    pdl_launch_dependents();
     if (!FROM_GRID) {
-        fill_axis_tables(p, xs, ys);
+        fill_axis_tables(p, xs, ys);                 // pure arithmetic: overlaps the tail of the previous kernel
         __syncthreads();
     }
+    pdl_wait();
     const int n = blockIdx.x / p.ctas_per_crop;
     const int tile = blockIdx.x - n * p.ctas_per_crop;
     const int npx = p.oH * p.oW;
@@ -156,12 +158,14 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     q += sizeof(float) * ((p.oW + p.oH + 1) & ~1);
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
     const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
+    pdl_launch_dependents();
     fill_axis_tables(p, xs, ys);
     if (gx_cta && p.gx_zero_bytes) {
         float4 *z4 = reinterpret_cast<float4 *>(zero_plane);
         for (int e = threadIdx.x; e < p.gx_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    pdl_wait();                                    // everything above touches shared memory only
     if (gx_cta) {
         // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop.  The
         // CTA's single barrier also tells everybody whether any crop of the frame needs the fallback.
@@ -186,22 +190,29 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
 // ------------------------------------------------------------------------------------------ host launchers
 static int pick_channel_group(int C) { return C == 1 ? 1 : (C % 3 == 0 ? 3 : 4); }
 
+template <typename YT, int CG, bool FROM_GRID, bool EXACT>
+static cudaError_t launch_fwd_tt(const CropParams &p, dim3 grid, size_t smem, cudaStream_t s)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, 0);
+    return cudaLaunchKernelEx(&cfg, stn_fwd_kernel<YT, CG, FROM_GRID, EXACT>, p);
+}
+
 template <typename YT, bool FROM_GRID>
 static cudaError_t launch_fwd_t(const CropParams &p, int cgsel, dim3 grid, size_t smem, cudaStream_t s)
 {
     const bool exact = p.C == cgsel;
     switch (cgsel) {
-    case 1: stn_fwd_kernel<YT, 1, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p); break;          // C == 1
-    case 3:
-        if (exact) stn_fwd_kernel<YT, 3, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p);
-        else stn_fwd_kernel<YT, 3, FROM_GRID, false><<<grid, kThreads, smem, s>>>(p);
-        break;
-    default:
-        if (exact) stn_fwd_kernel<YT, 4, FROM_GRID, true><<<grid, kThreads, smem, s>>>(p);
-        else stn_fwd_kernel<YT, 4, FROM_GRID, false><<<grid, kThreads, smem, s>>>(p);
-        break;
+    case 1: return launch_fwd_tt<YT, 1, FROM_GRID, true>(p, grid, smem, s);          // C == 1
+    case 3: return exact ? launch_fwd_tt<YT, 3, FROM_GRID, true>(p, grid, smem, s) : launch_fwd_tt<YT, 3, FROM_GRID, false>(p, grid, smem, s);
+    default: return exact ? launch_fwd_tt<YT, 4, FROM_GRID, true>(p, grid, smem, s) : launch_fwd_tt<YT, 4, FROM_GRID, false>(p, grid, smem, s);
     }
-    return cudaGetLastError();
 }
 
 int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stream)
@@ -248,13 +259,9 @@ static cudaError_t launch_bwd_tt(const CropParams &p, const CUtensorMap &gx_map,
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = fill_launch_attrs(attr, cs);
     return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT>, p, gx_map);
 }
 
