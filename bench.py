@@ -376,6 +376,44 @@ def run_ours(args):
             "fwd_us": ms_af * 1e3, "bwd_us": ms_ab * 1e3,
             "whole_step_frac": (fwd_bytes + bwd_bytes) / (ms_a * 1e-3) / 1e9}
 
+    # ---- SURVEY.md section 8(f) rows built so far, timed on the same buffers: prepare_images (rank 1), corner points (rank 2)
+    next_rows = {}
+    if not args.no_variants:
+        prep_out = torch.empty_like(sets[0]["x"])
+
+        def prep(e):                                   # output into the set's own gx buffer: rotating, so the writes reach DRAM
+            _lib.check(L.loans_stn_prepare_images(p(e["x"]), 255.0, p(e["gx"] if need_gx else prep_out), B, C, H, Wd,
+                                                  torch.cuda.current_stream().cuda_stream), "prepare_images")
+        if C == 3:
+            prep(sets[0])
+            g_prep = capture(lambda: [prep(e) for e in sets])
+            for _ in range(3):
+                g_prep.replay()
+            reps_p = max(1, steps // S)
+            ms_p = timed(lambda: [g_prep.replay() for _ in range(reps_p)]) / (reps_p * S)
+            pb = 8 * B * C * H * Wd
+            next_rows["prepare_images"] = {"us": ms_p * 1e3, "frames_per_s": world * B / (ms_p * 1e-3),
+                                           "algorithmic_bytes": pb, "achieved_gbs": pb / (ms_p * 1e-3) / 1e9,
+                                           "what": "SheepLocalizer.prepare_images as one kernel (uint8 quantise, RGB->BGR, mean), x*255 folded in"}
+        cor = torch.empty((N, 2, 2, 2), dtype=torch.float32, device=dev)
+        gcor = torch.randn((N, 2, 2, 2), dtype=torch.float32, device=dev)
+
+        def step_corners(e):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.loans_stn_crop_fwd_corners(p(e["x"]), p(e["theta"]), float(mask01), p(e["y"]), p(cor), N, K, C, H, Wd, oH, oW,
+                                                    dt_code, st), "crop_fwd_corners")
+            _lib.check(L.loans_stn_crop_bwd_corners(p(e["x"]), p(e["theta"]), float(mask01), p(e["gy"]), p(gcor), p(e["gtheta"]),
+                                                    p(e["gx"]), N, K, C, H, Wd, oH, oW, dt_code, st), "crop_bwd_corners")
+        step_corners(sets[0])
+        g_cor = capture(lambda: [step_corners(e) for e in sets])
+        for _ in range(3):
+            g_cor.replay()
+        reps_c = max(1, steps // S)
+        ms_c = timed(lambda: [g_cor.replay() for _ in range(reps_c)]) / (reps_c * S)
+        next_rows["corner_points"] = {"us_per_step": ms_c * 1e3, "value": world * N / (ms_c * 1e-3), "unit": UNIT,
+                                      "what": "fwd+bwd with points reduced to the grid's four corners (no dense grid written), "
+                                              "corner gradient folded into gtheta"}
+
     # ---- the reference's GPU path on the same inputs: cuDNN's spatial-transformer kernels (what chainer calls on a GPU)
     gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cudnn and K == 1 and not bf16 and need_gx:
@@ -499,7 +537,7 @@ def run_ours(args):
                               + ("plain launches" if args.no_pdl else "programmatic dependent launch (griddepcontrol) between consecutive kernels"),
                     "band_backward": args.band}),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
-                "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "variants": variants}
+                "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "variants": variants, "next_rows": next_rows}
         for v in variants.values():
             v["whole_step_frac"] = v["whole_step_frac"] / peak
         print(json.dumps(line), flush=True)

@@ -79,6 +79,15 @@ int loans_stn_configure(int key, int value);
  *      test: ratio, :33-35) so the RNG stream stays the host framework's.  In-place (out == in) allowed. */
 int loans_stn_rotation_dropout(const float *theta_in, float mask01, float *theta_out, int n, void *stream);
 
+/* ---- f1  SheepLocalizer.prepare_images (reference sheep/sheep_localizer.py:45,72-82): the localizer's per-step
+ *      device -> host -> device round trip with a per-image Python loop around chainer's resnet.prepare(image,
+ *      size=None), as one streaming kernel:  out[b,ch,i,j] = float(uint8(x[b,2-ch,i,j] * scale)) - mean[ch],
+ *      uint8() = C-cast truncation, mean = (103.063, 115.903, 123.152) for output channels B, G, R.
+ *      scale = 1: x is what the reference hands the method (`images.copy() * 255`); scale = 255: x is the raw [0,1]
+ *      frame batch and the caller's multiply is folded in.  x, out (b,3,h,w) f32, out != x.  No backward: the
+ *      reference takes no gradient through it (it builds new arrays on the host). */
+int loans_stn_prepare_images(const float *x, float scale, float *out, int b, int c, int h, int w, void *stream);
+
 /* ---- a2  F.spatial_transformer_grid forward / backward (call site sheep/sheep_localizer.py:62,170;
  *      arithmetic in chainer 4.1.0 chainer/functions/array/spatial_transformer_grid.py, restated in
  *      oracle/stn_numpy.py:grid_forward/grid_backward). */
@@ -109,6 +118,20 @@ int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y
 int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const void *gy,
                        const float *ggrid_upstream, float *gtheta, float *gx, float *ggrid_out,
                        int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
+
+/* ---- f2  the composite with the grid reduced to its four corner points.
+ *      Everything LoANs does with `points` besides sampling reads only grid[:, :, {0,-1}, {0,-1}]: the direction and
+ *      out-of-image regularisers (reference common/utils.py:141-178,301-316), extract_corners (sheep/sheep_localizer.py:
+ *      84-91), the evaluator (sheep/sheep_evaluator.py:17-30).  corners (n,2,2,2) f32 = grid[:, :, {0,oh-1}, {0,ow-1}],
+ *      bit-identical to those elements of the dense grid and itself a valid (n,2,2,2) `points` array for every one of those
+ *      consumers (they take height and width from its shape).  The dense grid (8*oh*ow bytes per crop, written in the
+ *      forward and read back as ggrid_upstream in the backward) is then never materialised.
+ *      bwd: gcorners (n,2,2,2) or NULL = gradient arriving on those four points, folded into gtheta. */
+int loans_stn_crop_fwd_corners(const float *x, const float *theta, float mask01, void *y, float *corners,
+                               int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream);
+int loans_stn_crop_bwd_corners(const float *x, const float *theta, float mask01, const void *gy,
+                               const float *gcorners, float *gtheta, float *gx,
+                               int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
 
 #ifdef __cplusplus
 }

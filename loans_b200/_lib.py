@@ -29,12 +29,15 @@ SIGNATURES = {
     "loans_stn_launch_count": [],
     "loans_stn_configure": [_i, _i],
     "loans_stn_rotation_dropout": [_vp, _fl, _vp, _i, _vp],
+    "loans_stn_prepare_images": [_vp, _fl, _vp, _i, _i, _i, _i, _vp],
     "loans_stn_grid_fwd": [_vp, _vp, _i, _i, _i, _vp],
     "loans_stn_grid_bwd": [_vp, _vp, _i, _i, _i, _vp],
     "loans_stn_sampler_fwd": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_sampler_bwd": [_vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_crop_fwd": [_vp, _vp, _fl, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_crop_bwd": [_vp, _vp, _fl, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_crop_fwd_corners": [_vp, _vp, _fl, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_crop_bwd_corners": [_vp, _vp, _fl, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
 }
 
 

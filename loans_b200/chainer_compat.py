@@ -210,6 +210,29 @@ if HAVE_CHAINER:                                         # pragma: no cover
         return SpatialTransformerSampler().apply((x, grid))[0]
 
 
+if HAVE_CHAINER:                                         # pragma: no cover
+
+    def prepare_images(self, images):
+        """Drop-in for SheepLocalizer.prepare_images / Resnet50SheepLocalizer.prepare_images (reference
+        sheep/sheep_localizer.py:72-82): same input (`images.copy() * 255`, a Variable on the GPU), same output
+        (a Variable holding the BGR, mean-subtracted float32 batch on the same device), no host round trip."""
+        x = images.data if isinstance(images, chainer.Variable) else images
+        _gpu_only(x)
+        x = cuda.cupy.ascontiguousarray(x, dtype=cuda.cupy.float32)
+        out = cuda.cupy.empty_like(x)
+        b, c, h, w = x.shape
+        with cuda.get_device_from_array(x):
+            _lib.check(_lib.lib().loans_stn_prepare_images(_ptr(x), 1.0, _ptr(out), b, c, h, w, _stream()),
+                       "loans_stn_prepare_images")
+        return chainer.Variable(out)
+
+    def patch_localizers(*classes):
+        """After `from sheep.sheep_localizer import SheepLocalizer, Resnet50SheepLocalizer`:
+        `patch_localizers(SheepLocalizer, Resnet50SheepLocalizer)` replaces their prepare_images method."""
+        for cls in classes:
+            cls.prepare_images = prepare_images
+
+
 def install():
     """Rebind the three operator names the reference uses.  Call before importing sheep.sheep_localizer."""
     _require()

@@ -38,7 +38,8 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
 int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not a band shape, use the general kernel
-void band_tuning(int which, int value);      // -1: shape not supported, use the general kernel
+void band_tuning(int which, int value);
+int launch_prepare_images(const float *x, float *out, float scale, int b, int h, int w, cudaStream_t stream);      // -1: shape not supported, use the general kernel
 
 static std::atomic<int> g_force_general{0};
 static std::atomic<int> g_tma_forward{0};
@@ -83,6 +84,22 @@ static CropParams base_params(int n, int k, int c, int h, int w, int oh, int ow)
     return p;
 }
 
+static int crop_bwd_dispatch(const CropParams &p, float mask01, int k, int c, int w, const float *gx, int gy_dtype, cudaStream_t stream)
+{
+    // mask01 == 0 (LoANs' ratio = 0.0), one crop per frame, gx wanted: the band backward -- every crop pixel evaluated
+    // once, gx written once by the band that owns the frame rows (stn_band.cu); crops it declines run the general roles
+    // inside the same launch.  Measured on B200 (profiles/README.md) it wins where frame rows are wide (512-px frames:
+    // 192 vs 209 us at BASELINE config 3), ties at config 2 and loses at config 5, so by default it is taken for frame
+    // rows of at least 4 KiB per channel group; LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on / off.
+    const int band = g_band_backward.load();
+    const bool band_shape = (long long)w * c * (long long)sizeof(float) >= 4096;
+    if (mask01 == 0.0f && k == 1 && gx != nullptr && (band == 1 || (band < 0 && band_shape)) && !g_force_general.load()) {
+        const int rc = launch_crop_bwd_band(p, gy_dtype, stream);
+        if (rc >= 0) return rc;
+    }
+    return launch_crop_bwd(p, gy_dtype, stream);
+}
+
 }  // namespace stn
 
 using namespace stn;
@@ -123,6 +140,19 @@ int loans_stn_rotation_dropout(const float *theta_in, float mask01, float *theta
     REQUIRE_PTR(what, theta_out);
     if (need_device(what)) return 1;
     return launch_rotation_dropout(theta_in, mask01, theta_out, n, (cudaStream_t)stream);
+}
+
+int loans_stn_prepare_images(const float *x, float scale, float *out, int b, int c, int h, int w, void *stream)
+{
+    const char *what = "loans_stn_prepare_images";
+    if (check_dims(what, b, 1, c, h, w, 1, 1)) return 1;
+    if (c != 3) return set_error("%s: frames must have 3 channels (RGB -> BGR), got %d", what, c);
+    if (b == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, out);
+    if (x == out) return set_error("%s: in-place is not possible (the channel order is reversed)", what);
+    if (need_device(what)) return 1;
+    return launch_prepare_images(x, out, scale, b, h, w, (cudaStream_t)stream);
 }
 
 int loans_stn_grid_fwd(const float *theta, float *grid, int n, int oh, int ow, void *stream)
@@ -200,6 +230,40 @@ int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y
     return launch_crop_fwd(p, false, y_dtype, (cudaStream_t)stream);
 }
 
+int loans_stn_crop_fwd_corners(const float *x, const float *theta, float mask01, void *y, float *corners,
+                               int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_fwd_corners";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, y_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, y);
+    REQUIRE_PTR(what, corners);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.y = y; p.corners_out = corners;
+    return launch_crop_fwd(p, false, y_dtype, (cudaStream_t)stream);
+}
+
+int loans_stn_crop_bwd_corners(const float *x, const float *theta, float mask01, const void *gy,
+                               const float *gcorners, float *gtheta, float *gx,
+                               int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_bwd_corners";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, gy_dtype)) return 1;
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, gy);
+    REQUIRE_PTR(what, gtheta);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.gcorners = gcorners;
+    p.gtheta = gtheta; p.gx = gx;
+    return crop_bwd_dispatch(p, mask01, k, c, w, gx, gy_dtype, (cudaStream_t)stream);
+}
+
 int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const void *gy,
                        const float *ggrid_upstream, float *gtheta, float *gx, float *ggrid_out,
                        int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream)
@@ -215,18 +279,7 @@ int loans_stn_crop_bwd(const float *x, const float *theta, float mask01, const v
     CropParams p = base_params(n, k, c, h, w, oh, ow);
     p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.ggrid_up = ggrid_upstream;
     p.gtheta = gtheta; p.gx = gx; p.ggrid_out = ggrid_out;
-    // mask01 == 0 (LoANs' ratio = 0.0), one crop per frame, gx wanted: the band backward -- every crop pixel evaluated
-    // once, gx written once by the band that owns the frame rows (stn_band.cu); crops it declines run the general roles
-    // inside the same launch.  Measured on B200 (profiles/README.md) it wins where frame rows are wide (512-px frames:
-    // 192 vs 209 us at BASELINE config 3), ties at config 2 and loses at config 5, so by default it is taken for frame
-    // rows of at least 4 KiB per channel group; LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on / off.
-    const int band = g_band_backward.load();
-    const bool band_shape = (long long)w * c * (long long)sizeof(float) >= 4096;
-    if (mask01 == 0.0f && k == 1 && gx != nullptr && (band == 1 || (band < 0 && band_shape)) && !g_force_general.load()) {
-        const int rc = launch_crop_bwd_band(p, gy_dtype, (cudaStream_t)stream);
-        if (rc >= 0) return rc;
-    }
-    return launch_crop_bwd(p, gy_dtype, (cudaStream_t)stream);
+    return crop_bwd_dispatch(p, mask01, k, c, w, gx, gy_dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -25,6 +25,8 @@ struct CropParams {
     float *gtheta;           // (N,2,3)
     float *gx;               // (B,C,H,W) or null
     float *ggrid_out;        // (N,2,oH,oW) or null
+    float *corners_out;      // (N,2,2,2) or null: the grid at its four corners [., ., {0,oH-1}, {0,oW-1}] (forward)
+    const float *gcorners;   // (N,2,2,2) or null: gradient arriving on those four grid points (backward)
     int N, K, C, H, W, oH, oW;
     double xstep, ystep;     // 2/(oW-1), 2/(oH-1)
     int px_per_cta;          // crop pixels handled by one CTA of the per-crop roles

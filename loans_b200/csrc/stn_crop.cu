@@ -58,6 +58,15 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
     YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * C * npx;
     float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
     const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
+    if (!FROM_GRID && p.corners_out && tile == 0 && threadIdx.x < 4) {
+        // the four corner points of the grid, the only ones LoANs' regularisers and box extraction read (reference
+        // common/utils.py:141-159, sheep/sheep_localizer.py:84-91): same operations as the dense grid, so bit-identical
+        const int ci = threadIdx.x >> 1, cj = threadIdx.x & 1;
+        const float xv = xs[cj ? p.oW - 1 : 0], yv = ys[ci ? p.oH - 1 : 0];
+        float *co = p.corners_out + 8 * (size_t)n + 2 * ci + cj;
+        co[0] = grid_elem(th.t00, th.t01, th.t02, xv, yv);
+        co[4] = grid_elem(th.t10, th.t11, th.t12, xv, yv);
+    }
 
     if (EXACT) {
         // one channel group covers all channels: two pixels per thread in flight -- both pixels' 8*CG tap loads are

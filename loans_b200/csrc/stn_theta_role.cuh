@@ -60,19 +60,34 @@ __device__ __forceinline__ void reduce_gtheta(const CropParams &p, const float (
         sm.part[threadIdx.x] = tot;
     }
     float *out = p.gtheta + 6 * (size_t)n;
+    // gradient arriving on the four corner points of the grid (loans_stn_crop_bwd_corners): gtheta += gc . [xs; ys; 1]^T
+    auto corner_term = [&](int k) {
+        if (!p.gcorners) return 0.f;
+        const float *gc = p.gcorners + 8 * (size_t)n + 4 * (k / 3);
+        const int m = k % 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ci = q >> 1, cj = q & 1;
+            const float w = m == 0 ? lin_x_at(p, cj ? p.oW - 1 : 0) : (m == 1 ? lin_y_at(p, ci ? p.oH - 1 : 0) : 1.0f);
+            acc = fmaf(__ldg(gc + q), w, acc);
+        }
+        return acc;
+    };
     if (cs > 1) {
         cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
         cl.sync();                                         // every CTA's part[] is written and visible
         if (rank == 0 && threadIdx.x < 6) {
             float tot = 0.f;
             for (int r = 0; r < cs; ++r) tot += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
+            tot += corner_term(threadIdx.x);
             // backward of the rotation mask: [0,1] and [1,0] are scaled (functions/rotation_droput.py:48)
             if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
             out[threadIdx.x] = tot;
         }
         cl.sync();                                         // peers keep their shared memory until rank 0 has read it
     } else if (threadIdx.x < 6) {
-        float tot = sm.part[threadIdx.x];
+        float tot = sm.part[threadIdx.x] + corner_term(threadIdx.x);
         if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
         out[threadIdx.x] = tot;
     }

@@ -51,19 +51,27 @@ def _out_hw(output_shape):
 # ------------------------------------------------------------------------------------------ fused a5
 class _StnCrop(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, theta, mask01, oh, ow, k, out_dtype, want_grid):
+    def forward(ctx, x, theta, mask01, oh, ow, k, out_dtype, points):
+        # points: 0 = crops only, 1 = crops + dense grid (N,2,oH,oW), 2 = crops + the grid's four corner points (N,2,2,2)
         x = x.contiguous()
         theta = theta.contiguous()
         b, c, h, w = x.shape
         n = theta.shape[0]
         y = torch.empty((n, c, oh, ow), dtype=out_dtype, device=x.device)
-        grid = torch.empty((n, 2, oh, ow), dtype=torch.float32, device=x.device) if want_grid else None
+        grid = None
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().loans_stn_crop_fwd(_ptr(x), _ptr(theta), mask01, _ptr(y), _ptr(grid),
-                                                     n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
-                       "loans_stn_crop_fwd")
+            if points == 2:
+                grid = torch.empty((n, 2, 2, 2), dtype=torch.float32, device=x.device)
+                _lib.check(_lib.lib().loans_stn_crop_fwd_corners(_ptr(x), _ptr(theta), mask01, _ptr(y), _ptr(grid),
+                                                                 n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_fwd_corners")
+            else:
+                grid = torch.empty((n, 2, oh, ow), dtype=torch.float32, device=x.device) if points == 1 else None
+                _lib.check(_lib.lib().loans_stn_crop_fwd(_ptr(x), _ptr(theta), mask01, _ptr(y), _ptr(grid),
+                                                         n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_fwd")
         ctx.save_for_backward(x, theta)
-        ctx.meta = (mask01, oh, ow, k, out_dtype)
+        ctx.meta = (mask01, oh, ow, k, out_dtype, points)
         if grid is None:
             return y
         return y, grid
@@ -71,7 +79,7 @@ class _StnCrop(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, ggrid=None):
         x, theta = ctx.saved_tensors
-        mask01, oh, ow, k, out_dtype = ctx.meta
+        mask01, oh, ow, k, out_dtype, points = ctx.meta
         b, c, h, w = x.shape
         n = theta.shape[0]
         need_gx = ctx.needs_input_grad[0]
@@ -85,10 +93,16 @@ class _StnCrop(torch.autograd.Function):
         if ggrid is not None:
             ggrid = ggrid.contiguous().float()
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().loans_stn_crop_bwd(_ptr(x), _ptr(theta), mask01, _ptr(gy), _ptr(ggrid),
-                                                     _ptr(gtheta), _ptr(gx), None,
-                                                     n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
-                       "loans_stn_crop_bwd")
+            if points == 2:
+                _lib.check(_lib.lib().loans_stn_crop_bwd_corners(_ptr(x), _ptr(theta), mask01, _ptr(gy), _ptr(ggrid),
+                                                                 _ptr(gtheta), _ptr(gx),
+                                                                 n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_bwd_corners")
+            else:
+                _lib.check(_lib.lib().loans_stn_crop_bwd(_ptr(x), _ptr(theta), mask01, _ptr(gy), _ptr(ggrid),
+                                                         _ptr(gtheta), _ptr(gx), None,
+                                                         n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_bwd")
         return gx, gtheta, None, None, None, None, None, None
 
 
@@ -100,13 +114,17 @@ def _check_sampler_types(x, theta_or_grid, grid_like):
 
 
 def stn_crop(x, theta, output_shape, ratio=None, crops_per_frame=1, out_dtype=torch.float32,
-             return_grid=True, mask01=None):
+             return_grid=True, mask01=None, points="grid"):
     """rotation_dropout(theta, ratio) -> grid -> sampler in one kernel (reference sheep/sheep_localizer.py:61-63).
 
     x (B,C,H,W) float32 frames; theta (B*K,2,3) float32; ``ratio`` as in ``rotation_dropout`` (``None``: no
     dropout node in front of the grid); ``mask01`` overrides the drawn mask value (tests, data-parallel runs
     that broadcast one draw to all ranks).  Returns ``(rois, points)`` like the localizer does (``rois`` only
     if ``return_grid`` is false).  ``out_dtype`` torch.float32 or torch.bfloat16 (= bf16(fp32 result)).
+    ``points="corners"``: ``points`` is the grid at its four corners only, shape (N,2,2,2) -- bit-identical to
+    ``grid[:, :, [0,-1]][:, :, :, [0,-1]]`` and a valid ``points`` array for everything LoANs does with it besides
+    sampling (regularisers, extract_corners, evaluator: they index ``[0,0]``, ``[0,width-1]``, ``[height-1,0]``,
+    ``[-1,-1]`` with height and width taken from its shape); the dense grid is never written or read back.
     """
     from loans_b200.functions.rotation_droput import draw_mask_value
     _need_cuda(x, theta)
@@ -120,7 +138,10 @@ def stn_crop(x, theta, output_shape, ratio=None, crops_per_frame=1, out_dtype=to
     oh, ow = _out_hw(output_shape)
     if mask01 is None:
         mask01 = 1.0 if ratio is None else draw_mask_value(ratio)
-    return _StnCrop.apply(x, theta, float(mask01), oh, ow, k, out_dtype, bool(return_grid))
+    if points not in ("grid", "corners"):
+        raise ValueError("points must be 'grid' or 'corners'")
+    mode = 0 if not return_grid else (2 if points == "corners" else 1)
+    return _StnCrop.apply(x, theta, float(mask01), oh, ow, k, out_dtype, mode)
 
 
 # ------------------------------------------------------------------------------------------ a2

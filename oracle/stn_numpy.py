@@ -28,7 +28,7 @@ import numpy as np
 __all__ = [
     "rotation_dropout_mask_value", "rotation_dropout_forward", "rotation_dropout_backward",
     "grid_coords", "grid_forward", "grid_backward", "sampler_forward", "sampler_backward",
-    "crop_forward", "crop_backward",
+    "crop_forward", "crop_backward", "prepare_images", "RESNET_MEAN_BGR", "grid_corners", "corners_to_dense_ggrid",
 ]
 
 
@@ -218,3 +218,48 @@ def crop_backward(x, theta, output_shape, gy, ggrid_upstream=None, mask_value=1.
     total = ggrid if ggrid_upstream is None else ggrid + np.asarray(ggrid_upstream, dtype=np.float32)
     gtheta = rotation_dropout_backward(grid_backward(total), np.float32(mask_value))
     return gtheta, gx, ggrid
+
+
+# --------------------------------------------------------------------------- f1: prepare_images
+RESNET_MEAN_BGR = np.array([103.063, 115.903, 123.152], dtype=np.float32)
+
+
+def prepare_images(scaled_images):
+    """SheepLocalizer.prepare_images (sheep/sheep_localizer.py:72-82) applied to what the caller hands it,
+    ``images.copy() * 255`` (:45): per image ``chainer.links.model.vision.resnet.prepare(image, size=None)``, stacked.
+
+    resnet.prepare lives in chainer 4.1.0 (third party, not in /root/reference; PARITY UNPINNED for the mean constants,
+    restated from the published source): ndarray (3,H,W) -> transpose to (H,W,3) -> ``astype(numpy.uint8)`` ->
+    ``Image.fromarray`` -> ``convert('RGB')`` (a no-op for an RGB array) -> ``numpy.asarray(image, float32)`` ->
+    ``image[:, :, ::-1]`` (RGB -> BGR) -> ``image -= [103.063, 115.903, 123.152]`` -> transpose to (3,H,W).
+    tests/test_oracle.py checks this restatement against the literal PIL chain.
+    """
+    scaled_images = np.asarray(scaled_images)
+    assert scaled_images.ndim == 4 and scaled_images.shape[1] == 3
+    out = []
+    for image in scaled_images:                                   # F.separate(images, axis=0)  :77
+        image = image.transpose((1, 2, 0)).astype(np.uint8)       # truncation toward zero
+        image = np.asarray(image, dtype=np.float32)
+        image = image[:, :, ::-1]
+        image = image - RESNET_MEAN_BGR
+        out.append(image.transpose((2, 0, 1)))
+    return np.stack(out, axis=0)                                  # F.stack  :78
+
+
+# --------------------------------------------------------------------------- f2: the grid's four corner points
+def grid_corners(grid):
+    """grid (N,2,oH,oW) -> (N,2,2,2): the points LoANs reads besides sampling -- [0,0], [0,W-1], [H-1,0] in
+    LossCalculator.get_corners (common/utils.py:141-159) and [0,0], [-1,-1] in extract_corners
+    (sheep/sheep_localizer.py:84-91)."""
+    return np.ascontiguousarray(grid[:, :, [0, -1]][:, :, :, [0, -1]])
+
+
+def corners_to_dense_ggrid(gcorners, out_h, out_w):
+    """The gradient arriving on those four points as the dense upstream grid gradient the reference would see
+    (zeros elsewhere; coinciding corners of a 1-row / 1-column crop add up, as get_item's backward does)."""
+    n = gcorners.shape[0]
+    gg = np.zeros((n, 2, out_h, out_w), np.float32)
+    for ci, i in enumerate((0, out_h - 1)):
+        for cj, j in enumerate((0, out_w - 1)):
+            gg[:, :, i, j] += gcorners[:, :, ci, cj]
+    return gg

@@ -15,6 +15,12 @@
    Chainer 4.1.0 (where this arithmetic lives) is absent, so these vectors are ORACLE-DERIVED: they
    guard the oracle and the CUDA path against drift, they do not pin them to Chainer.
 
+3. ``prepare_images.npz`` -- SheepLocalizer.prepare_images (reference sheep/sheep_localizer.py:72-82): the literal
+   statement sequence of chainer 4.1.0's ``resnet.prepare(image, size=None)`` (uint8 cast, PIL ``Image.fromarray`` /
+   ``convert('RGB')``, float32, BGR flip, mean subtraction) executed with the real PIL on seeded frames, including
+   values on the quantisation boundaries.  Chainer is absent, so the statement sequence and the mean constants are
+   restated from the published source (parity unpinned for them); PIL's part is executed, not restated.
+
 /root/reference is read at generation time only; nothing under tests/ reads it at test time.
 """
 import importlib.util
@@ -151,6 +157,36 @@ def make_stn_small():
     print("stn_small.npz:", len(shapes), "cases (oracle-derived, torch cross-checked)")
 
 
+def make_prepare_images():
+    from PIL import Image
+    rng = np.random.default_rng(4242)
+    out = {}
+    shapes = [(2, 3, 5, 7), (1, 3, 8, 8), (3, 3, 9, 12), (2, 3, 1, 3)]
+    for i, shp in enumerate(shapes):
+        x = rng.random(shp, dtype=np.float32)
+        if i == 1:                                    # exact quantisation boundaries k / 255 and their float32 neighbours
+            k = rng.integers(0, 256, shp).astype(np.float32)
+            x = (k / np.float32(255)).astype(np.float32)
+            x[..., ::2] = np.nextafter(x[..., ::2], np.float32(0))
+            x[0, 0, 0, :4] = [0.0, 1.0, 0.5, 1.0 / 255]
+        scaled = x * 255                              # images.copy() * 255, sheep/sheep_localizer.py:45
+        res = []
+        for image in scaled:
+            im = image.transpose((1, 2, 0))
+            im = Image.fromarray(im.astype(np.uint8))
+            im = im.convert('RGB')
+            im = np.asarray(im, dtype=np.float32)
+            im = im[:, :, ::-1]
+            im = im - np.array([103.063, 115.903, 123.152], dtype=np.float32)
+            res.append(im.transpose((2, 0, 1)))
+        out["c%d_x" % i] = x
+        out["c%d_out" % i] = np.stack(res, axis=0)
+    out["n_cases"] = np.int64(len(shapes))
+    np.savez_compressed(os.path.join(HERE, "prepare_images.npz"), **out)
+    print("prepare_images.npz:", len(shapes), "cases (literal resnet.prepare statement sequence through PIL)")
+
+
 if __name__ == "__main__":
     make_rotation_dropout()
     make_stn_small()
+    make_prepare_images()

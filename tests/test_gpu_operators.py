@@ -212,3 +212,95 @@ def test_host_buffer_pipeline_matches_oracle(T):
         assert np.array_equal(o["y"].numpy(), y0) and np.array_equal(o["grid"].numpy(), g0)
         assert np.abs(o["gx"].numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max()
         assert np.abs(o["gtheta"].numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max()
+
+
+# ------------------------------------------------------------------------------------------------ f1: prepare_images
+def test_prepare_images_on_device_matches_oracle_and_pil_golden(T):
+    """SheepLocalizer.prepare_images as one kernel: bit-exact against the oracle and the PIL-produced fixtures, both as
+    the drop-in for the method (input already * 255) and with the multiply folded in; vector and scalar paths."""
+    import os
+    import torch
+    from loans_b200.functions import prepare_images
+    from oracle import stn_numpy as on
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "prepare_images.npz"))
+    for i in range(int(g["n_cases"])):
+        x = g["c%d_x" % i]
+        xd = torch.from_numpy(x).cuda()
+        assert np.array_equal(prepare_images(xd * 255).cpu().numpy(), g["c%d_out" % i])
+        assert np.array_equal(prepare_images(xd, scale=255).cpu().numpy(), g["c%d_out" % i])
+    rng = np.random.default_rng(5)
+    for shp in ((4, 3, 224, 224), (2, 3, 75, 75), (3, 3, 33, 17), (1, 3, 512, 512)):
+        x = rng.random(shp, dtype=np.float32)
+        ref = on.prepare_images(x * 255)
+        xd = torch.from_numpy(x).cuda()
+        out = prepare_images(xd, scale=255)
+        assert out.dtype == torch.float32 and not out.requires_grad
+        assert np.array_equal(out.cpu().numpy(), ref)
+        # an unaligned view: the scalar path
+        big = torch.zeros(x.size + 1, dtype=torch.float32, device="cuda")
+        view = big[1:].view(shp)
+        view.copy_(xd)
+        assert np.array_equal(prepare_images(view, scale=255).cpu().numpy(), ref)
+    with pytest.raises(Exception):
+        prepare_images(torch.zeros((1, 4, 8, 8), device="cuda"))
+    with pytest.raises(Exception):
+        prepare_images(torch.zeros((1, 3, 8, 8)))                 # CPU tensor: refused, no fallback
+
+
+# ------------------------------------------------------------------------------------------------ f2: corner points
+@pytest.mark.parametrize("name,batch,mask", [("cfg1", None, 0.0), ("cfg2", 8, 1.0), ("cfg3", 3, 0.0), ("cfg4", 2, 0.0)])
+def test_corner_points_replace_the_dense_grid(T, name, batch, mask):
+    """points='corners': (N,2,2,2), bit-identical to the dense grid's corner elements; a gradient arriving on them gives
+    the gtheta the reference would get from the dense grid with that gradient at its corners; LoANs' consumers index it
+    exactly as they index the dense grid."""
+    from loans_b200.functions import stn_crop
+    from oracle import stn_numpy as on
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True)
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    rng = np.random.default_rng(3)
+    n = d["theta"].shape[0]
+    gc = rng.standard_normal((n, 2, 2, 2)).astype(np.float32)
+    x, th = _t(T, d["x"], grad=True), _t(T, d["theta"], grad=True)
+    rois, corners = stn_crop(x, th, osz, mask01=mask, crops_per_frame=k, points="corners")
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, mask, k)
+    assert corners.shape == (n, 2, 2, 2)
+    assert np.array_equal(rois.detach().cpu().numpy(), y0)
+    assert np.array_equal(corners.detach().cpu().numpy(), on.grid_corners(grid0))
+    # the reference's consumers, written as they are there, on either array
+    for pts, (hh, ww) in ((corners.detach().cpu().numpy(), (2, 2)), (grid0, osz)):
+        tl = pts[:, 0, 0, 0], pts[:, 1, 0, 0]
+        tr = pts[:, 0, 0, ww - 1]
+        bl = pts[:, 1, hh - 1, 0]
+        br = pts[:, 0, -1, -1], pts[:, 1, -1, -1]
+        if pts.shape[2] == 2:
+            got = (tl, tr, bl, br)
+        else:
+            want = (tl, tr, bl, br)
+    for a, b in zip(got, want):
+        for u, v in zip(np.atleast_2d(a), np.atleast_2d(b)):
+            assert np.array_equal(u, v)
+    T.autograd.backward([rois, corners], [_t(T, d["gy"]), _t(T, gc)])
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], on.corners_to_dense_ggrid(gc, *osz), mask, k)
+    gt, gx = th.grad.cpu().numpy(), x.grad.cpu().numpy()
+    assert np.abs(gt - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
+    assert np.abs(gx - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())
+
+
+def test_corner_points_of_one_row_crops(T):
+    from loans_b200.functions import stn_crop
+    from oracle import stn_numpy as on
+    rng = np.random.default_rng(8)
+    for osz in ((1, 5), (6, 1), (1, 1)):
+        x = rng.random((3, 3, 16, 20), dtype=np.float32)
+        theta = W.make_theta(rng, 3)
+        gy = rng.standard_normal((3, 3) + osz).astype(np.float32)
+        gc = rng.standard_normal((3, 2, 2, 2)).astype(np.float32)
+        xt, tt = _t(T, x), _t(T, theta, grad=True)
+        rois, corners = stn_crop(xt, tt, osz, mask01=1.0, points="corners")
+        _, grid0 = oc.crop_forward(x, theta, osz, 1.0, 1)
+        assert np.array_equal(corners.detach().cpu().numpy(), on.grid_corners(grid0))
+        T.autograd.backward([rois, corners], [_t(T, gy), _t(T, gc)])
+        gt0, _, _ = oc.crop_backward(x, theta, osz, gy, on.corners_to_dense_ggrid(gc, *osz), 1.0, 1)
+        assert np.abs(tt.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())

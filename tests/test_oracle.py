@@ -239,3 +239,23 @@ def test_shard_invariance():
         gts, gxs, _ = oc.crop_backward(d["x"][lo:hi], d["theta"][lo:hi], osz, d["gy"][lo:hi])
         assert np.array_equal(ys, y[lo:hi]) and np.array_equal(gs, grid[lo:hi])
         assert np.array_equal(gts, gt[lo:hi]) and np.array_equal(gxs, gx[lo:hi])
+
+
+# ------------------------------------------------------------------------------------------------ f1: prepare_images
+def test_prepare_images_matches_the_pil_golden():
+    """oracle/stn_numpy.prepare_images vs fixtures produced by the literal resnet.prepare statement sequence run
+    through the real PIL (tests/golden/make_golden.py), quantisation boundaries included."""
+    g = np.load(os.path.join(GOLDEN, "prepare_images.npz"))
+    for i in range(int(g["n_cases"])):
+        x = g["c%d_x" % i]
+        out = on.prepare_images(x * 255)
+        assert out.dtype == np.float32 and np.array_equal(out, g["c%d_out" % i])
+
+
+def test_prepare_images_semantics():
+    x = np.zeros((1, 3, 2, 2), np.float32)
+    x[0, 0] = 1.0                                    # pure red frame
+    out = on.prepare_images(x * 255)
+    assert np.allclose(out[0, 2], 255 - 123.152) and np.allclose(out[0, 0], -103.063) and np.allclose(out[0, 1], -115.903)
+    y = np.full((1, 3, 1, 1), 0.999, np.float32)     # 254.745 truncates to 254, it does not round to 255
+    assert on.prepare_images(y * 255)[0, 0, 0, 0] == np.float32(254) - np.float32(103.063)
