@@ -14,6 +14,7 @@ CFG_FORCE_GENERAL = 1
 CFG_TMA_FORWARD = 2
 CFG_BAND_BACKWARD = 3
 CFG_PDL = 8
+CFG_THETA_FIRST = 9
 CFG_BAND_CS, CFG_BAND_ROWS, CFG_BAND_TILE_KB, CFG_BAND_VARIANT = 4, 5, 6, 7
 
 _lib = None
@@ -83,6 +84,10 @@ def tma_forward(on):
 def pdl(on):
     """Programmatic dependent launch of the fused kernels (default on)."""
     check(lib().loans_stn_configure(CFG_PDL, int(bool(on))), "loans_stn_configure")
+
+
+def theta_first(on):
+    check(lib().loans_stn_configure(CFG_THETA_FIRST, int(bool(on))), "loans_stn_configure")
 
 
 def band_backward(on):

@@ -33,6 +33,7 @@ struct CropParams {
     int ctas_per_crop;       // == cluster size in the backward theta role
     // backward gx role: CTAs [0, gx_ctas), eight warp-owned tiles of one frame each; the rest reduce gtheta
     int gx_ctas, gx_ctas_per_frame, gx_tiles_per_frame, gx_tiles_x;
+    int theta_ctas, theta_first;   // theta_first: the theta-role CTAs take the low block indices (scheduled first)
     int gx_tile_rows, gx_tile_cols, gx_tile_pitch, gx_tile_bytes;
     int gx_vec4;             // 128-bit stores of gx are legal (W % 4 == 0, aligned base)
     int gx_tma_store;        // tiles leave shared memory through TMA tensor stores (map passed next to this struct)
@@ -101,6 +102,8 @@ int set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);
 bool pdl_enabled();
+bool theta_first_enabled();
+int gx_tiles_per_warp_override();
 // fills the launch attributes shared by the fused kernels: [cluster dimension,] programmatic stream serialisation
 inline unsigned fill_launch_attrs(cudaLaunchAttribute *attr, unsigned cluster)
 {

@@ -152,6 +152,22 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ backward
+#ifdef STN_BAND_TRACE
+// debug build only: per-CTA timestamps (globaltimer ns) of the general backward, 8 slots per CTA
+__device__ long long *g_bwd_trace = nullptr;
+__device__ __forceinline__ void bwd_trace(int slot, long long v = -1)
+{
+    if (threadIdx.x == 0 && g_bwd_trace) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_bwd_trace[(size_t)blockIdx.x * 8 + slot] = v >= 0 ? v : t;
+    }
+}
+#define BTRACE(...) bwd_trace(__VA_ARGS__)
+#else
+#define BTRACE(...)
+#endif
+
 template <typename GT, int CG, bool EXACT>
 __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p, const __grid_constant__ CUtensorMap gx_map)
 {
@@ -166,7 +182,10 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     float *ys = xs + p.oW;
     q += sizeof(float) * ((p.oW + p.oH + 1) & ~1);
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q);
-    const bool gx_cta = (int)blockIdx.x < p.gx_ctas;
+    // role of this CTA and its index inside the role; which role is scheduled first is a launch parameter
+    const bool gx_cta = p.theta_first ? (int)blockIdx.x >= p.theta_ctas : (int)blockIdx.x < p.gx_ctas;
+    const int role_idx = (int)blockIdx.x - (p.theta_first ? (gx_cta ? p.theta_ctas : 0) : (gx_cta ? 0 : p.gx_ctas));
+    BTRACE(0);
     pdl_launch_dependents();
     fill_axis_tables(p, xs, ys);
     if (gx_cta && p.gx_zero_bytes) {
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
     if (gx_cta) {
         // per-crop geometry of this CTA's frame (float32, conservative); P == 0 marks a gather-fallback crop.  The
         // CTA's single barrier also tells everybody whether any crop of the frame needs the fallback.
-        const int b = blockIdx.x / p.gx_ctas_per_frame;
+        const int b = role_idx / p.gx_ctas_per_frame;
         int fallback = 0;
         if (b < p.N / p.K)
             for (int kk = threadIdx.x; kk < p.K; kk += kThreads) {
@@ -188,12 +207,25 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
             }
         const int any_fallback = __syncthreads_or(fallback);
         if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
+        BTRACE(1);
         gx_role<GT, CG, EXACT>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles, zero_plane, b,
-                               (int)blockIdx.x - b * p.gx_ctas_per_frame, p.gx_tiles_per_warp);
+                               role_idx - b * p.gx_ctas_per_frame, p.gx_tiles_per_warp);
+        BTRACE(2);
+        BTRACE(4, 1);
     } else {
         __syncthreads();
-        theta_role<GT, CG, EXACT>(p, xs, ys, sm, (int)blockIdx.x - p.gx_ctas);
+        BTRACE(1);
+        theta_role<GT, CG, EXACT>(p, xs, ys, sm, role_idx);
+        BTRACE(2);
+        BTRACE(4, 2);
     }
+#ifdef STN_BAND_TRACE
+    {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        BTRACE(5, (long long)smid);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ host launchers
@@ -357,6 +389,7 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
             long long tpw = all_tiles / ((long long)kWarps * kNumSMs * 6 * p.K);     // K crops per frame: K times the work per tile
             if (tpw < 1) tpw = 1;
             if (tpw > STN_GX_MAX_TILES_PER_WARP) tpw = STN_GX_MAX_TILES_PER_WARP;
+            if (gx_tiles_per_warp_override() > 0) tpw = gx_tiles_per_warp_override();
             p.gx_tiles_per_warp = (int)tpw;
         }
         p.gx_ctas_per_frame = (p.gx_tiles_per_frame + kWarps * p.gx_tiles_per_warp - 1) / (kWarps * p.gx_tiles_per_warp);
@@ -377,6 +410,8 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         smem += (size_t)p.gx_tile_bytes + p.gx_zero_bytes + sizeof(ScatterGeom) * (size_t)p.K;
     }
     p.gx_ctas = (int)gx_ctas;
+    p.theta_ctas = (int)theta_ctas;
+    p.theta_first = theta_first_enabled() ? 1 : 0;
     const long long ctas = theta_ctas + gx_ctas;
     if (ctas > 0x7fffffffLL) return set_error("crop_bwd: too many CTAs (%lld)", ctas);
     if (smem > 200 * 1024) return set_error("crop_bwd: %d crops per frame need %zu B of shared memory (max 200 KiB)", p.K, smem);
@@ -386,5 +421,13 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     if (e != cudaSuccess) return set_error("crop_bwd launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
+
+#ifdef STN_BAND_TRACE
+extern "C" int loans_stn_debug_bwd_trace(void *buf)
+{
+    long long *q = reinterpret_cast<long long *>(buf);
+    return cudaMemcpyToSymbol(g_bwd_trace, &q, sizeof(q)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // namespace stn

@@ -62,9 +62,14 @@ def main():
         reps = 40 if name == "cfg2" else 8
         _, bwd_bytes = W.algorithmic_bytes(wl, need_gx=True)
         _lib.band_backward(False)
-        us = time_bwd(wl, sets, reps)
-        print(json.dumps({"wl": name, "kernel": "general", "us": round(us, 2), "gbs": round(bwd_bytes / us / 1e3, 1)}), flush=True)
+        for tpw in [int(v) for v in os.environ.get("SWEEP_TPW", "0").split(",")]:
+            _lib.check(_lib.lib().loans_stn_configure(10, tpw), "cfg")
+            us = time_bwd(wl, sets, reps)
+            print(json.dumps({"wl": name, "kernel": "general", "tiles_per_warp": tpw, "us": round(us, 2), "gbs": round(bwd_bytes / us / 1e3, 1)}), flush=True)
+        _lib.check(_lib.lib().loans_stn_configure(10, 0), "cfg")
         _lib.band_backward(True)
+        if os.environ.get("SWEEP", "x") == "":
+            continue
         combos = os.environ.get("SWEEP", "0,1,2;8;0;0;0,1,2,3").split(";")
         variants, css, tiles, rowss, flagss = [[int(v) for v in c.split(",")] for c in combos]
         for variant0 in variants:
