@@ -67,10 +67,12 @@ def _cpu_worker(task):
     """Runs in a spawned process: numpy restatement of the reference's CPU path, fwd+bwd, on its own shard."""
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
-    name, frames, seed, need_gx, seconds, reps = task
+    name, frames, seed, need_gx, seconds, reps = task[:6]
     from loans_b200 import workloads as W
     from oracle import stn_numpy as on
     wl = W.WORKLOADS[name]
+    if len(task) > 6:                                  # rotation-dropout ratio of the arm being mirrored
+        wl = wl._replace(rotation_ratio=task[6])
     d = W.make_inputs(wl, seed=seed, batch=frames)
     osz = (wl.out_h, wl.out_w)
     mask = 1.0 if wl.rotation_ratio is None else float(wl.rotation_ratio)
@@ -93,7 +95,7 @@ def _cpu_worker(task):
     return frames * k * reps, el
 
 
-def cpu_baseline(wl_name, need_gx, seconds):
+def cpu_baseline(wl_name, need_gx, seconds, ratio=0.0):
     """All host cores, one process each (the numpy path is single-threaded by construction), every process
     working through its own 8-frame shard of the workload for ~`seconds`; rate = sum of per-process rates."""
     import multiprocessing as mp
@@ -103,7 +105,7 @@ def cpu_baseline(wl_name, need_gx, seconds):
     frames = max(1, min(8, wl.batch))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(wl_name, frames, 1234 + i, need_gx, seconds, None) for i in range(cores)], chunksize=1)
+        res = pool.map(_cpu_worker, [(wl_name, frames, 1234 + i, need_gx, seconds, None, ratio) for i in range(cores)], chunksize=1)
     rate = sum(c / t for c, t in res)
     one = max(c / t for c, t in res)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -114,8 +116,8 @@ def cpu_baseline(wl_name, need_gx, seconds):
 
 
 def _ref_step_worker(task):
-    name, frames, seed = task
-    return _cpu_worker((name, frames, seed, True, 0.0, 1))
+    name, frames, seed, ratio = task
+    return _cpu_worker((name, frames, seed, True, 0.0, 1, ratio))
 
 
 def run_reference(args):
@@ -127,11 +129,13 @@ def run_reference(args):
     import multiprocessing as mp
     from loans_b200 import workloads as W
     wl = W.WORKLOADS[args.workload]
+    rr = args.rotation_ratio                       # the same config as our arm: LoANs' ratio 0.0 unless asked otherwise
+    wl = wl._replace(rotation_ratio=0.0 if rr == "shipped" else (None if rr == "none" else float(rr)))
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, wl.batch))
     base, extra = divmod(wl.batch, procs)
     shards = [base + (1 if i < extra else 0) for i in range(procs)]
-    tasks = [(wl.name, f, 1234 + i) for i, f in enumerate(shards)]
+    tasks = [(wl.name, f, 1234 + i, wl.rotation_ratio) for i, f in enumerate(shards)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
         for _ in range(max(1, args.warmup)):
@@ -240,7 +244,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, need_gx, args.cpu_seconds)      # before CUDA is touched: plain host work
+        cpu = cpu_baseline(args.workload, need_gx, args.cpu_seconds, wl.rotation_ratio)      # before CUDA is touched: plain host work
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
