@@ -414,6 +414,24 @@ def run_ours(args):
             g_cor.replay()
         reps_c = max(1, steps // S)
         ms_c = timed(lambda: [g_cor.replay() for _ in range(reps_c)]) / (reps_c * S)
+        if C == 3:
+            yg = torch.empty((N, 1, oH, oW), dtype=ydt, device=dev)
+            gyg = torch.randn((N, 1, oH, oW), dtype=torch.float32, device=dev).to(ydt)
+
+            def step_gray(e):
+                st = torch.cuda.current_stream().cuda_stream
+                _lib.check(L.loans_stn_crop_fwd_ex(p(e["x"]), p(e["theta"]), float(mask01), p(yg), None, p(cor), _lib.FLAG_GRAY,
+                                                   N, K, C, H, Wd, oH, oW, dt_code, st), "crop_fwd_ex")
+                _lib.check(L.loans_stn_crop_bwd_ex(p(e["x"]), p(e["theta"]), float(mask01), p(gyg), None, p(gcor), p(e["gtheta"]),
+                                                   p(e["gx"]), None, _lib.FLAG_GRAY, N, K, C, H, Wd, oH, oW, dt_code, st), "crop_bwd_ex")
+            step_gray(sets[0])
+            g_gray = capture(lambda: [step_gray(e) for e in sets])
+            for _ in range(3):
+                g_gray.replay()
+            ms_g = timed(lambda: [g_gray.replay() for _ in range(reps_c)]) / (reps_c * S)
+            next_rows["grayscale_corners"] = {"us_per_step": ms_g * 1e3, "value": world * N / (ms_g * 1e-3), "unit": UNIT,
+                                              "what": "fwd+bwd with the localizer's grayscale epilogue fused (1-channel crops "
+                                                      "and gy) and corner points"}
         next_rows["corner_points"] = {"us_per_step": ms_c * 1e3, "value": world * N / (ms_c * 1e-3), "unit": UNIT,
                                       "what": "fwd+bwd with points reduced to the grid's four corners (no dense grid written), "
                                               "corner gradient folded into gtheta"}
@@ -447,12 +465,31 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("%s%s" % (wl.name, "" if need_gx else "_nogx"), {}).get("bwd_dram_bytes")
+    # ---- the DRAM write rate of this GPU, measured here: zero-fill of the rotating gx buffers (plain torch fill kernels, a
+    # calibration like MEASURED_PEAKS.json's copy, not part of the path).  The backward is write-dominated (gx is dense) and a
+    # B200 sustains markedly fewer bytes/s of pure writes than of copy traffic, so the copy peak overstates what it can reach.
+    write_cal = None
+    if need_gx:
+        g_fill = capture(lambda: [e["gx"].zero_() for e in sets])
+        for _ in range(3):
+            g_fill.replay()
+        reps_w = max(1, steps // S)
+        ms_w = timed(lambda: [g_fill.replay() for _ in range(reps_w)]) / (reps_w * S)
+        gx_bytes = 4 * B * C * H * Wd
+        write_gbs = gx_bytes / (ms_w * 1e-3) / 1e9
+        read_bytes = bwd_bytes - gx_bytes
+        floor_us = (gx_bytes / write_gbs + read_bytes / peak) / 1e3
+        write_cal = {"write_gbs_measured": write_gbs, "fill_us": ms_w * 1e3, "bwd_written_bytes": gx_bytes,
+                     "bwd_read_bytes": read_bytes, "bwd_dram_floor_us": floor_us,
+                     "bwd_frac_of_dram_floor": floor_us / (ms_b * 1e3),
+                     "note": "floor = gx bytes at the measured pure-write rate + the algorithmic read bytes at the copy peak"}
     ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9
     ach_f = fwd_bytes / (ms_f * 1e-3) / 1e9
     ach_s = (fwd_bytes + bwd_bytes) / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "backward launch: stn_bwd_kernel (gx role + cluster-reduced theta role), or stn_bwd_band_kernel where the band backward is taken (mask01 == 0, wide frame rows)",
                 "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_us": ms_b * 1e3,
+                "write_bound": write_cal,
                 "fwd_kernel": {"achieved": ach_f, "frac": ach_f / peak, "algorithmic_bytes_per_launch": fwd_bytes,
                                "avg_launch_us": ms_f * 1e3},
                 "whole_step": {"achieved": ach_s, "frac": ach_s / peak, "algorithmic_bytes": fwd_bytes + bwd_bytes,

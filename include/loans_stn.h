@@ -135,6 +135,20 @@ int loans_stn_crop_bwd_corners(const float *x, const float *theta, float mask01,
                                const float *gcorners, float *gtheta, float *gx,
                                int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
 
+/* ---- f3  the composite with every optional input / output and the localizer's grayscale epilogue (SURVEY.md section
+ *      8f rank 3; reference sheep/sheep_localizer.py:65-68, `transform_rois_to_grayscale`):
+ *          b, g, r = F.split_axis(rois, 3, axis=1);  rois = 0.299 * r + 0.587 * g + 0.114 * b
+ *      flags & LOANS_STN_FLAG_GRAY (c == 3): y / gy are (n,1,oh,ow); the three channels are mixed in registers (float32
+ *      products summed left to right, channel 0 taken as b, channel 2 as r, exactly as above) and the backward hands
+ *      coef[ch] * gy to channel ch, so the 3-channel crops are never written or read.  grid, corners (fwd) and
+ *      ggrid_upstream, gcorners, gx, ggrid_out (bwd) may each be NULL.  With flags == 0 these are the entry points above. */
+#define LOANS_STN_FLAG_GRAY 1
+int loans_stn_crop_fwd_ex(const float *x, const float *theta, float mask01, void *y, float *grid, float *corners,
+                          int flags, int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream);
+int loans_stn_crop_bwd_ex(const float *x, const float *theta, float mask01, const void *gy, const float *ggrid_upstream,
+                          const float *gcorners, float *gtheta, float *gx, float *ggrid_out,
+                          int flags, int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libloans_stn.so")
 ABI_VERSION = 1
 F32, BF16 = 0, 1
+FLAG_GRAY = 1
 CFG_FORCE_GENERAL = 1
 CFG_TMA_FORWARD = 2
 CFG_BAND_BACKWARD = 3
@@ -37,6 +38,8 @@ SIGNATURES = {
     "loans_stn_sampler_bwd": [_vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_crop_fwd": [_vp, _vp, _fl, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_crop_bwd": [_vp, _vp, _fl, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
+    "loans_stn_crop_fwd_ex": [_vp, _vp, _fl, _vp, _vp, _vp] + [_i] * 9 + [_vp],
+    "loans_stn_crop_bwd_ex": [_vp, _vp, _fl, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 9 + [_vp],
     "loans_stn_crop_fwd_corners": [_vp, _vp, _fl, _vp, _vp] + [_i] * 8 + [_vp],
     "loans_stn_crop_bwd_corners": [_vp, _vp, _fl, _vp, _vp, _vp, _vp] + [_i] * 8 + [_vp],
 }

@@ -236,6 +236,45 @@ int loans_stn_crop_fwd(const float *x, const float *theta, float mask01, void *y
     return launch_crop_fwd(p, false, y_dtype, (cudaStream_t)stream);
 }
 
+int loans_stn_crop_fwd_ex(const float *x, const float *theta, float mask01, void *y, float *grid, float *corners,
+                          int flags, int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_fwd_ex";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, y_dtype)) return 1;
+    if (flags & ~LOANS_STN_FLAG_GRAY) return set_error("%s: unknown flags 0x%x", what, flags);
+    if ((flags & LOANS_STN_FLAG_GRAY) && c != 3) return set_error("%s: the grayscale epilogue needs 3 channels, got %d", what, c);
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, y);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.y = y; p.grid_out = grid; p.corners_out = corners;
+    p.gray = (flags & LOANS_STN_FLAG_GRAY) ? 1 : 0;
+    return launch_crop_fwd(p, false, y_dtype, (cudaStream_t)stream);
+}
+
+int loans_stn_crop_bwd_ex(const float *x, const float *theta, float mask01, const void *gy, const float *ggrid_upstream,
+                          const float *gcorners, float *gtheta, float *gx, float *ggrid_out,
+                          int flags, int n, int k, int c, int h, int w, int oh, int ow, int gy_dtype, void *stream)
+{
+    const char *what = "loans_stn_crop_bwd_ex";
+    if (check_dims(what, n, k, c, h, w, oh, ow) || check_dtype(what, gy_dtype)) return 1;
+    if (flags & ~LOANS_STN_FLAG_GRAY) return set_error("%s: unknown flags 0x%x", what, flags);
+    if ((flags & LOANS_STN_FLAG_GRAY) && c != 3) return set_error("%s: the grayscale epilogue needs 3 channels, got %d", what, c);
+    if (n == 0) return 0;
+    REQUIRE_PTR(what, x);
+    REQUIRE_PTR(what, theta);
+    REQUIRE_PTR(what, gy);
+    REQUIRE_PTR(what, gtheta);
+    if (need_device(what)) return 1;
+    CropParams p = base_params(n, k, c, h, w, oh, ow);
+    p.x = x; p.theta = theta; p.mask01 = mask01; p.gy = gy; p.ggrid_up = ggrid_upstream; p.gcorners = gcorners;
+    p.gtheta = gtheta; p.gx = gx; p.ggrid_out = ggrid_out;
+    p.gray = (flags & LOANS_STN_FLAG_GRAY) ? 1 : 0;
+    return crop_bwd_dispatch(p, mask01, k, c, w, gx, gy_dtype, (cudaStream_t)stream);
+}
+
 int loans_stn_crop_fwd_corners(const float *x, const float *theta, float mask01, void *y, float *corners,
                                int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream)
 {

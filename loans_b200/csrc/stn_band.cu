@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
         const int row_elems = max(r1 - r0, 0) * p.oW;
         const int lines = (row_elems * (int)sizeof(GT) + 127) / 128;
-        for (int e = tid; e < lines * CG; e += kThreads) {
+        const int gplanes = p.gray ? 1 : CG;
+        for (int e = tid; e < lines * gplanes; e += kThreads) {
             const int ch = e / lines, l = e - ch * lines;
-            const char *a = reinterpret_cast<const char *>(reinterpret_cast<const GT *>(p.gy) + ((size_t)n * CG + ch) * p.oH * p.oW +
+            const char *a = reinterpret_cast<const char *>(reinterpret_cast<const GT *>(p.gy) + ((size_t)n * gplanes + ch) * p.oH * p.oW +
                                                            (size_t)r0 * p.oW) + (size_t)l * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     const int plane = H * W;
     const size_t fpx = (size_t)plane;
     const float *xb = p.x + (size_t)n * CG * fpx;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * CG * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (p.gray ? 1 : CG) * npx;
     float *gxb = p.gx + (size_t)n * CG * fpx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch) {
                 load_taps(xb + ch * plane, ta, W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
-                px.g[ch] = Elem<GT>::load(gp, ch * npx);
+                px.g[ch] = load_gy<GT>(gp, ch, npx, p.gray);
             }
         };
         auto reduce = [&](const Px &px) {                             // gtheta sums and ggrid: own rows only

@@ -27,6 +27,7 @@ struct CropParams {
     float *ggrid_out;        // (N,2,oH,oW) or null
     float *corners_out;      // (N,2,2,2) or null: the grid at its four corners [., ., {0,oH-1}, {0,oW-1}] (forward)
     const float *gcorners;   // (N,2,2,2) or null: gradient arriving on those four grid points (backward)
+    int gray;                // C == 3 only: y / gy are (N,1,oH,oW), y = 0.299*ch2 + 0.587*ch1 + 0.114*ch0 (see gray_coef)
     int N, K, C, H, W, oH, oW;
     double xstep, ystep;     // 2/(oW-1), 2/(oH-1)
     int px_per_cta;          // crop pixels handled by one CTA of the per-crop roles
@@ -63,6 +64,23 @@ template <> struct Elem<__nv_bfloat16> {
         p[i] = __float2bfloat16_rn(v);
     }
 };
+
+// Grayscale epilogue of the localizer (reference sheep/sheep_localizer.py:65-68, transform_rois_to_grayscale):
+//     b, g, r = F.split_axis(rois, 3, axis=1);  rois = 0.299 * r + 0.587 * g + 0.114 * b
+// i.e. channel 0 is taken as b and channel 2 as r, float32 products, summed left to right; the backward hands
+// coef[ch] * ggray to channel ch (MulConstant's backward).
+__device__ __forceinline__ float gray_coef(int ch) { return ch == 0 ? 0.114f : (ch == 1 ? 0.587f : 0.299f); }
+__device__ __forceinline__ float gray_mix(float c0, float c1, float c2)
+{
+    return f_add(f_add(f_mul(0.299f, c2), f_mul(0.587f, c1)), f_mul(0.114f, c0));
+}
+// upstream gradient of channel ch at crop pixel q: gy[ch][q], or coef[ch] * ggray[q] behind the grayscale epilogue.
+// base = this crop's gy (channel 0 of the channel group at hand), npx = oH*oW
+template <typename GT>
+__device__ __forceinline__ float load_gy(const GT *base, int ch, int npx, int gray)
+{
+    return gray ? f_mul(gray_coef(ch), Elem<GT>::load(base, 0)) : Elem<GT>::load(base, (size_t)ch * npx);
+}
 
 // xs[0..oW) and ys[0..oH) into shared memory (numpy.linspace(-1,1,n,dtype=float32), see stn_math.cuh)
 __device__ __forceinline__ void fill_axis_tables(float *xs, float *ys, int oW, int oH, double xstep, double ystep)

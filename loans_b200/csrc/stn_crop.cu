@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
     if (!FROM_GRID) th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * C * plane;
-    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * C * npx;
+    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * (p.gray ? 1 : C) * npx;
     float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
     const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
     if (!FROM_GRID && p.corners_out && tile == 0 && threadIdx.x < 4) {
@@ -102,6 +102,13 @@ __global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const __grid_constant
         };
         auto finish = [&](const Px &px) {
             if (!px.live) return;
+            if (CG == 3 && p.gray) {                   // grayscale epilogue: one output channel
+                float c[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) c[ch] = interp(px.wt, px.v[ch % CG][0], px.v[ch % CG][1], px.v[ch % CG][2], px.v[ch % CG][3]);
+                Elem<YT>::store(yb + px.q, 0, gray_mix(c[0], c[1], c[2]));
+                return;
+            }
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
                 Elem<YT>::store(yb + px.q, ch * npx, interp(px.wt, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]));

@@ -9,9 +9,18 @@
 
 namespace stn {
 
+// gy element i of a crop for the per-frame-pixel gather (i = channel * plane + pixel); behind the grayscale epilogue
+// every channel reads the single gray plane, scaled by its coefficient
 template <typename GT>
 struct GyLoader {
-    __device__ __forceinline__ float operator()(const GT *p, size_t i) const { return Elem<GT>::load(p, i); }
+    size_t plane;
+    int gray, c0;
+    __device__ __forceinline__ float operator()(const GT *p, size_t i) const
+    {
+        if (!gray) return Elem<GT>::load(p, i);
+        const int ch = (int)(i / plane);
+        return f_mul(gray_coef(c0 + ch), Elem<GT>::load(p, i - (size_t)ch * plane));
+    }
 };
 
 #ifndef STN_BWD_MIN_CTAS
@@ -72,7 +81,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                 __syncwarp();
                 touched = true;
             }
-            const GT *gyc = gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
+            const GT *gyc = p.gray ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
             for (int cp = 0; cp < P; ++cp)
@@ -92,7 +101,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                         float gv[CG];
                         const GT *gp = gyc + i * p.oW + j;
 #pragma unroll
-                        for (int ch = 0; ch < CG; ++ch) gv[ch] = ch < nc ? Elem<GT>::load(gp, ch * npx) : 0.f;
+                        for (int ch = 0; ch < CG; ++ch) gv[ch] = ch < nc ? load_gy<GT>(gp, ch, npx, p.gray) : 0.f;
                         ScatterTaps st;
                         if (!scatter_taps(th, xs[j], ys[i], p.H, p.W, r0, tr, s0, tw, st)) continue;
                         const Tap &t = st.t;
@@ -204,8 +213,10 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
                 const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
                 if (make_scatter_geom(th, p.H, p.W, p.oH, p.oW).P != 0) continue;
                 const InvCrop inv = make_inv_crop(th, p.H, p.W, p.oH, p.oW);
+                const GyLoader<GT> ld = {(size_t)npx, p.gray, c0};
                 gather_from_crop<CG>(inv, xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
-                                     gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx, nc, GyLoader<GT>(), acc);
+                                     p.gray ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx,
+                                     nc, ld, acc);
             }
 #pragma unroll
         for (int ch = 0; ch < CG; ++ch)

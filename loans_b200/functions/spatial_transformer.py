@@ -51,16 +51,23 @@ def _out_hw(output_shape):
 # ------------------------------------------------------------------------------------------ fused a5
 class _StnCrop(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, theta, mask01, oh, ow, k, out_dtype, points):
+    def forward(ctx, x, theta, mask01, oh, ow, k, out_dtype, points, gray=False):
         # points: 0 = crops only, 1 = crops + dense grid (N,2,oH,oW), 2 = crops + the grid's four corner points (N,2,2,2)
         x = x.contiguous()
         theta = theta.contiguous()
         b, c, h, w = x.shape
         n = theta.shape[0]
-        y = torch.empty((n, c, oh, ow), dtype=out_dtype, device=x.device)
+        y = torch.empty((n, 1 if gray else c, oh, ow), dtype=out_dtype, device=x.device)
         grid = None
         with torch.cuda.device(x.device):
-            if points == 2:
+            if gray:
+                grid = (torch.empty((n, 2, 2, 2), dtype=torch.float32, device=x.device) if points == 2 else
+                        torch.empty((n, 2, oh, ow), dtype=torch.float32, device=x.device) if points == 1 else None)
+                _lib.check(_lib.lib().loans_stn_crop_fwd_ex(_ptr(x), _ptr(theta), mask01, _ptr(y),
+                                                            _ptr(grid) if points == 1 else None, _ptr(grid) if points == 2 else None,
+                                                            _lib.FLAG_GRAY, n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_fwd_ex")
+            elif points == 2:
                 grid = torch.empty((n, 2, 2, 2), dtype=torch.float32, device=x.device)
                 _lib.check(_lib.lib().loans_stn_crop_fwd_corners(_ptr(x), _ptr(theta), mask01, _ptr(y), _ptr(grid),
                                                                  n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
@@ -71,7 +78,7 @@ class _StnCrop(torch.autograd.Function):
                                                          n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
                            "loans_stn_crop_fwd")
         ctx.save_for_backward(x, theta)
-        ctx.meta = (mask01, oh, ow, k, out_dtype, points)
+        ctx.meta = (mask01, oh, ow, k, out_dtype, points, gray)
         if grid is None:
             return y
         return y, grid
@@ -79,21 +86,27 @@ class _StnCrop(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, ggrid=None):
         x, theta = ctx.saved_tensors
-        mask01, oh, ow, k, out_dtype, points = ctx.meta
+        mask01, oh, ow, k, out_dtype, points, gray = ctx.meta
         b, c, h, w = x.shape
         n = theta.shape[0]
         need_gx = ctx.needs_input_grad[0]
         gtheta = torch.empty_like(theta)
         gx = torch.empty_like(x) if need_gx else None
         if gy is None:
-            gy = torch.zeros((n, c, oh, ow), dtype=out_dtype, device=x.device)
+            gy = torch.zeros((n, 1 if gray else c, oh, ow), dtype=out_dtype, device=x.device)
         gy = gy.contiguous()
         if gy.dtype != out_dtype:
             gy = gy.to(out_dtype)
         if ggrid is not None:
             ggrid = ggrid.contiguous().float()
         with torch.cuda.device(x.device):
-            if points == 2:
+            if gray:
+                _lib.check(_lib.lib().loans_stn_crop_bwd_ex(_ptr(x), _ptr(theta), mask01, _ptr(gy),
+                                                            _ptr(ggrid) if points == 1 else None, _ptr(ggrid) if points == 2 else None,
+                                                            _ptr(gtheta), _ptr(gx), None, _lib.FLAG_GRAY,
+                                                            n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
+                           "loans_stn_crop_bwd_ex")
+            elif points == 2:
                 _lib.check(_lib.lib().loans_stn_crop_bwd_corners(_ptr(x), _ptr(theta), mask01, _ptr(gy), _ptr(ggrid),
                                                                  _ptr(gtheta), _ptr(gx),
                                                                  n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
@@ -103,7 +116,7 @@ class _StnCrop(torch.autograd.Function):
                                                          _ptr(gtheta), _ptr(gx), None,
                                                          n, k, c, h, w, oh, ow, _DT[out_dtype], _stream()),
                            "loans_stn_crop_bwd")
-        return gx, gtheta, None, None, None, None, None, None
+        return gx, gtheta, None, None, None, None, None, None, None
 
 
 def _check_sampler_types(x, theta_or_grid, grid_like):
@@ -114,7 +127,7 @@ def _check_sampler_types(x, theta_or_grid, grid_like):
 
 
 def stn_crop(x, theta, output_shape, ratio=None, crops_per_frame=1, out_dtype=torch.float32,
-             return_grid=True, mask01=None, points="grid"):
+             return_grid=True, mask01=None, points="grid", grayscale=False):
     """rotation_dropout(theta, ratio) -> grid -> sampler in one kernel (reference sheep/sheep_localizer.py:61-63).
 
     x (B,C,H,W) float32 frames; theta (B*K,2,3) float32; ``ratio`` as in ``rotation_dropout`` (``None``: no
@@ -125,6 +138,8 @@ def stn_crop(x, theta, output_shape, ratio=None, crops_per_frame=1, out_dtype=to
     ``grid[:, :, [0,-1]][:, :, :, [0,-1]]`` and a valid ``points`` array for everything LoANs does with it besides
     sampling (regularisers, extract_corners, evaluator: they index ``[0,0]``, ``[0,width-1]``, ``[height-1,0]``,
     ``[-1,-1]`` with height and width taken from its shape); the dense grid is never written or read back.
+    ``grayscale=True`` (3-channel frames): the localizer's ``transform_rois_to_grayscale`` epilogue
+    (sheep/sheep_localizer.py:65-68) fused in; ``rois`` is (N,1,oH,oW) = ``0.299*ch2 + 0.587*ch1 + 0.114*ch0``.
     """
     from loans_b200.functions.rotation_droput import draw_mask_value
     _need_cuda(x, theta)
@@ -141,7 +156,9 @@ def stn_crop(x, theta, output_shape, ratio=None, crops_per_frame=1, out_dtype=to
     if points not in ("grid", "corners"):
         raise ValueError("points must be 'grid' or 'corners'")
     mode = 0 if not return_grid else (2 if points == "corners" else 1)
-    return _StnCrop.apply(x, theta, float(mask01), oh, ow, k, out_dtype, mode)
+    if grayscale:
+        _expect(x.shape[1] == 3, "rois are not in RGB, can not convert them to grayscale (C == %d)" % x.shape[1])
+    return _StnCrop.apply(x, theta, float(mask01), oh, ow, k, out_dtype, mode, bool(grayscale))
 
 
 # ------------------------------------------------------------------------------------------ a2

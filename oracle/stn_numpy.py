@@ -28,7 +28,7 @@ import numpy as np
 __all__ = [
     "rotation_dropout_mask_value", "rotation_dropout_forward", "rotation_dropout_backward",
     "grid_coords", "grid_forward", "grid_backward", "sampler_forward", "sampler_backward",
-    "crop_forward", "crop_backward", "prepare_images", "RESNET_MEAN_BGR", "grid_corners", "corners_to_dense_ggrid",
+    "crop_forward", "crop_backward", "prepare_images", "RESNET_MEAN_BGR", "grid_corners", "corners_to_dense_ggrid", "grayscale_forward", "grayscale_backward",
 ]
 
 
@@ -263,3 +263,19 @@ def corners_to_dense_ggrid(gcorners, out_h, out_w):
         for cj, j in enumerate((0, out_w - 1)):
             gg[:, :, i, j] += gcorners[:, :, ci, cj]
     return gg
+
+
+# --------------------------------------------------------------------------- f3: the localizer's grayscale epilogue
+def grayscale_forward(rois):
+    """sheep/sheep_localizer.py:65-68: ``b, g, r = F.split_axis(rois, 3, axis=1); rois = 0.299 * r + 0.587 * g + 0.114 * b``
+    (chainer: the Python constants are cast to the array dtype, float32 products, summed left to right)."""
+    rois = np.asarray(rois)
+    assert rois.shape[1] == 3, "rois are not in RGB, can not convert them to grayscale"      # :66
+    b, g, r = rois[:, 0:1], rois[:, 1:2], rois[:, 2:3]
+    return np.float32(0.299) * r + np.float32(0.587) * g + np.float32(0.114) * b
+
+
+def grayscale_backward(ggray):
+    """gradient w.r.t. the 3-channel rois: MulConstant's backward is ``value * gy``, Add's passes gy through."""
+    ggray = np.asarray(ggray)
+    return np.concatenate([np.float32(0.114) * ggray, np.float32(0.587) * ggray, np.float32(0.299) * ggray], axis=1)

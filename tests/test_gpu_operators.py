@@ -304,3 +304,68 @@ def test_corner_points_of_one_row_crops(T):
         T.autograd.backward([rois, corners], [_t(T, gy), _t(T, gc)])
         gt0, _, _ = oc.crop_backward(x, theta, osz, gy, on.corners_to_dense_ggrid(gc, *osz), 1.0, 1)
         assert np.abs(tt.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
+
+
+# ------------------------------------------------------------------------------------------------ f3: grayscale epilogue
+@pytest.mark.parametrize("name,batch,mask,bf16", [("cfg1", None, 0.0, False), ("cfg2", 8, 1.0, False), ("cfg3", 4, 0.0, True),
+                                                   ("cfg3", 3, 0.0, False), ("cfg4", 2, 0.0, False)])
+def test_grayscale_epilogue_fused(T, name, batch, mask, bf16):
+    """transform_rois_to_grayscale (sheep/sheep_localizer.py:65-68) inside the crop kernels: rois (N,1,oH,oW) bit-exact
+    against the oracle's sampler followed by the reference's three statements; gradients equal to the oracle's backward fed
+    coef * ggray per channel (general kernel, band kernel at cfg3, K = 16 at cfg4)."""
+    from loans_b200.functions import stn_crop
+    from oracle import stn_numpy as on
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True)
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    n = d["theta"].shape[0]
+    rng = np.random.default_rng(12)
+    gg = rng.standard_normal((n, 1) + osz).astype(np.float32)
+    dt = T.bfloat16 if bf16 else T.float32
+    x, th = _t(T, d["x"], grad=True), _t(T, d["theta"], grad=True)
+    rois, points = stn_crop(x, th, osz, mask01=mask, crops_per_frame=k, out_dtype=dt, grayscale=True)
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, mask, k)
+    gray0 = on.grayscale_forward(y0)
+    assert rois.shape == (n, 1) + osz
+    got = rois.detach().float().cpu().numpy()
+    if bf16:
+        ref = T.from_numpy(gray0).to(T.bfloat16).float().numpy()
+        gg = T.from_numpy(gg).to(T.bfloat16).float().numpy()
+    else:
+        ref = gray0
+    assert np.array_equal(got, ref)
+    assert np.array_equal(points.detach().cpu().numpy(), grid0)
+    rois.backward(_t(T, gg).to(dt))
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, on.grayscale_backward(gg), None, mask, k)
+    assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
+    assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())
+
+
+def test_grayscale_needs_three_channels(T):
+    from loans_b200.functions import stn_crop
+    x = T.zeros((1, 4, 8, 8), device="cuda")
+    th = T.tensor([[[1.0, 0, 0], [0, 1.0, 0]]], device="cuda")
+    with pytest.raises(Exception):
+        stn_crop(x, th, (4, 4), grayscale=True)
+
+
+def test_grayscale_epilogue_on_degenerate_transforms(T):
+    """the per-frame-pixel gather fallback of the gx role (singular / wildly up-sampling transforms) behind the epilogue"""
+    from loans_b200.functions import stn_crop
+    from oracle import stn_numpy as on
+    thetas = np.array([[[0.5, 0.25, 0], [1.0, 0.5, 0.1]], [[0, 0, 0.2], [0, 0, -0.3]], [[0.05, 0.01, 0.3], [-0.01, 0.06, -0.2]],
+                       [[0.8, 0, 0], [0, 0.8, 0]], [[0.004, 0, 0.1], [0, 0.003, 0.2]]], np.float32)
+    rng = np.random.default_rng(21)
+    for shp, osz in (((5, 3, 24, 24), (9, 9)), ((5, 3, 16, 20), (12, 7))):
+        x = rng.random(shp, dtype=np.float32)
+        gg = rng.standard_normal((5, 1) + osz).astype(np.float32)
+        for mask in (1.0, 0.0):
+            xt, tt = _t(T, x, grad=True), _t(T, thetas, grad=True)
+            rois, _ = stn_crop(xt, tt, osz, mask01=mask, grayscale=True)
+            y0, _ = oc.crop_forward(x, thetas, osz, mask, 1)
+            assert np.array_equal(rois.detach().cpu().numpy(), on.grayscale_forward(y0))
+            rois.backward(_t(T, gg))
+            gt0, gx0, _ = oc.crop_backward(x, thetas, osz, on.grayscale_backward(gg), None, mask, 1)
+            assert np.abs(tt.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
+            assert np.abs(xt.grad.cpu().numpy() - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())

@@ -259,3 +259,18 @@ def test_prepare_images_semantics():
     assert np.allclose(out[0, 2], 255 - 123.152) and np.allclose(out[0, 0], -103.063) and np.allclose(out[0, 1], -115.903)
     y = np.full((1, 3, 1, 1), 0.999, np.float32)     # 254.745 truncates to 254, it does not round to 255
     assert on.prepare_images(y * 255)[0, 0, 0, 0] == np.float32(254) - np.float32(103.063)
+
+
+def test_grayscale_epilogue_semantics():
+    """sheep/sheep_localizer.py:65-68: channel 0 is taken as b, channel 2 as r; the backward is the transpose."""
+    rois = np.zeros((1, 3, 1, 2), np.float32)
+    rois[0, 2, 0, 0] = 1.0                           # "r" = channel 2
+    rois[0, 0, 0, 1] = 1.0                           # "b" = channel 0
+    g = on.grayscale_forward(rois)
+    assert g.shape == (1, 1, 1, 2) and g[0, 0, 0, 0] == np.float32(0.299) and g[0, 0, 0, 1] == np.float32(0.114)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((2, 3, 4, 5)).astype(np.float32)
+    gg = rng.standard_normal((2, 1, 4, 5)).astype(np.float32)
+    lhs = float((on.grayscale_forward(a).astype(np.float64) * gg).sum())
+    rhs = float((a.astype(np.float64) * on.grayscale_backward(gg)).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
