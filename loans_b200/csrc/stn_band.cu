@@ -57,7 +57,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // A crop the band plan declines: the cluster runs the general roles on it (tiles over the whole frame, then gtheta).
-template <typename GT, int CG>
+template <typename GT, int CG, bool GRAY>
 __device__ __noinline__ void band_declined(const CropParams &p, const Theta &th, unsigned char *smem_raw, BwdSmem &sm,
                                            float *xs, float *ys, ScatterGeom *geom, int n, int rank)
 {
@@ -68,13 +68,13 @@ __device__ __noinline__ void band_declined(const CropParams &p, const Theta &th,
         fb = geom[0].P == 0;
     }
     const int any_fb = __syncthreads_or(fb);
-    gx_role<GT, CG, true>(p, nullptr, xs, ys, any_fb != 0, geom, reinterpret_cast<float *>(smem_raw), nullptr, n, rank,
+    gx_role<GT, CG, true, GRAY>(p, nullptr, xs, ys, any_fb != 0, geom, reinterpret_cast<float *>(smem_raw), nullptr, n, rank,
                           p.band_fb_tiles_per_warp);
-    theta_role<GT, CG, true>(p, xs, ys, sm, (int)blockIdx.x);
+    theta_role<GT, CG, true, GRAY>(p, xs, ys, sm, (int)blockIdx.x);
 }
 
 // ILP = crop pixels in flight per thread, MINB = CTAs per SM the register budget is set for
-template <typename GT, int CG, int ILP, int MINB>
+template <typename GT, int CG, int ILP, int MINB, bool GRAY>
 __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
         const int row_elems = max(r1 - r0, 0) * p.oW;
         const int lines = (row_elems * (int)sizeof(GT) + 127) / 128;
-        const int gplanes = p.gray ? 1 : CG;
+        constexpr int gplanes = GRAY ? 1 : CG;
         for (int e = tid; e < lines * gplanes; e += kThreads) {
             const int ch = e / lines, l = e - ch * lines;
             const char *a = reinterpret_cast<const char *>(reinterpret_cast<const GT *>(p.gy) + ((size_t)n * gplanes + ch) * p.oH * p.oW +
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const BandCrop bc = make_band_crop(th, p.H, p.W, p.oH, p.oW);     // the same verdict in every CTA of the cluster
     if (!bc.ok) {
-        band_declined<GT, CG>(p, th, smem_raw, sm, xs, ys, geom, n, rank);
+        band_declined<GT, CG, GRAY>(p, th, smem_raw, sm, xs, ys, geom, n, rank);
         return;
     }
     TRACE(1);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     const int plane = H * W;
     const size_t fpx = (size_t)plane;
     const float *xb = p.x + (size_t)n * CG * fpx;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (p.gray ? 1 : CG) * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : CG) * npx;
     float *gxb = p.gx + (size_t)n * CG * fpx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch) {
                 load_taps(xb + ch * plane, ta, W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
-                px.g[ch] = load_gy<GT>(gp, ch, npx, p.gray);
+                px.g[ch] = load_gy<GT, GRAY>(gp, ch, npx);
             }
         };
         auto reduce = [&](const Px &px) {                             // gtheta sums and ggrid: own rows only
@@ -364,13 +364,13 @@ void band_tuning(int which, int value)
     else g_band_variant = value;
 }
 
-template <typename GT, int CG, int ILP, int MINB>
+template <typename GT, int CG, int ILP, int MINB, bool GRAY = false>
 static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;
         if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             granted = smem;
         }
@@ -383,7 +383,7 @@ static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned 
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, cs);
-    return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB>, p);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY>, p);
 }
 
 template <typename GT, int CG>
@@ -391,6 +391,9 @@ static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned c
 {
     // variant 0 (default): one crop pixel in flight per thread, 64 registers, four CTAs per SM -- the fastest at every
     // measured shape; variant 1: two pixels in flight, 80 registers, three CTAs per SM (kept for A/B runs)
+    if constexpr (CG == 3) {
+        if (p.gray) return launch_band_ttt<GT, 3, 1, 4, true>(p, ctas, cs, smem, s);   // grayscale epilogue: its own kernel
+    }
     switch (g_band_variant & 15) {
     case 1: return launch_band_ttt<GT, CG, 2, 3>(p, ctas, cs, smem, s);
     default: return launch_band_ttt<GT, CG, 1, 4>(p, ctas, cs, smem, s);

@@ -175,7 +175,7 @@ __device__ __forceinline__ void bwd_trace(int slot, long long v = -1)
 #define BTRACE(...)
 #endif
 
-template <typename GT, int CG, bool EXACT>
+template <typename GT, int CG, bool EXACT, bool GRAY>
 __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(const __grid_constant__ CropParams p, const __grid_constant__ CUtensorMap gx_map)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];       // TMA tensor stores read 128-byte aligned tiles
@@ -215,14 +215,14 @@ __global__ void __launch_bounds__(kThreads, STN_BWD_MIN_CTAS) stn_bwd_kernel(con
         const int any_fallback = __syncthreads_or(fallback);
         if (b >= p.N / p.K) return;                                            // padding CTA (cluster rounding)
         BTRACE(1);
-        gx_role<GT, CG, EXACT>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles, zero_plane, b,
+        gx_role<GT, CG, EXACT, GRAY>(p, &gx_map, xs, ys, any_fallback != 0, geom, tiles, zero_plane, b,
                                role_idx - b * p.gx_ctas_per_frame, p.gx_tiles_per_warp);
         BTRACE(2);
         BTRACE(4, 1);
     } else {
         __syncthreads();
         BTRACE(1);
-        theta_role<GT, CG, EXACT>(p, xs, ys, sm, role_idx);
+        theta_role<GT, CG, EXACT, GRAY>(p, xs, ys, sm, role_idx);
         BTRACE(2);
         BTRACE(4, 2);
     }
@@ -291,13 +291,13 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
     return 0;
 }
 
-template <typename GT, int CG, bool EXACT>
+template <typename GT, int CG, bool EXACT, bool GRAY = false>
 static cudaError_t launch_bwd_tt(const CropParams &p, const CUtensorMap &gx_map, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;                 // per template instance; only ever grows
         if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG, EXACT, GRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             granted = smem;
         }
@@ -310,7 +310,7 @@ static cudaError_t launch_bwd_tt(const CropParams &p, const CUtensorMap &gx_map,
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, cs);
-    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT>, p, gx_map);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_kernel<GT, CG, EXACT, GRAY>, p, gx_map);
 }
 
 template <typename GT>
@@ -319,7 +319,9 @@ static cudaError_t launch_bwd_t(const CropParams &p, const CUtensorMap &m, int c
     const bool exact = p.C == cgsel;
     switch (cgsel) {
     case 1: return launch_bwd_tt<GT, 1, true>(p, m, ctas, cs, smem, s);
-    case 3: return exact ? launch_bwd_tt<GT, 3, true>(p, m, ctas, cs, smem, s) : launch_bwd_tt<GT, 3, false>(p, m, ctas, cs, smem, s);
+    case 3:
+        if (exact && p.gray) return launch_bwd_tt<GT, 3, true, true>(p, m, ctas, cs, smem, s);      // grayscale epilogue: its own kernel
+        return exact ? launch_bwd_tt<GT, 3, true>(p, m, ctas, cs, smem, s) : launch_bwd_tt<GT, 3, false>(p, m, ctas, cs, smem, s);
     default: return exact ? launch_bwd_tt<GT, 4, true>(p, m, ctas, cs, smem, s) : launch_bwd_tt<GT, 4, false>(p, m, ctas, cs, smem, s);
     }
 }

@@ -11,15 +11,14 @@ namespace stn {
 
 // gy element i of a crop for the per-frame-pixel gather (i = channel * plane + pixel); behind the grayscale epilogue
 // every channel reads the single gray plane, scaled by its coefficient
-template <typename GT>
+template <typename GT, bool GRAY = false>
 struct GyLoader {
     size_t plane;
-    int gray, c0;
     __device__ __forceinline__ float operator()(const GT *p, size_t i) const
     {
-        if (!gray) return Elem<GT>::load(p, i);
+        if (!GRAY) return Elem<GT>::load(p, i);
         const int ch = (int)(i / plane);
-        return f_mul(gray_coef(c0 + ch), Elem<GT>::load(p, i - (size_t)ch * plane));
+        return f_mul(gray_coef(ch), Elem<GT>::load(p, i - (size_t)ch * plane));
     }
 };
 
@@ -33,7 +32,7 @@ __device__ __forceinline__ int div_small(int e, int d, float inv_d, bool small)
     return small ? __float2int_rz(((float)e + 0.5f) * inv_d) : e / d;
 }
 
-template <typename GT, int CG>
+template <typename GT, int CG, bool GRAY>
 __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys, const float *tile,
                                               float *gxb, const GT *gy, int b, int c0, int nc,
                                               int r0, int tr, int s0, int tw, bool any_fallback);
@@ -43,7 +42,7 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
 // with __syncwarp() only.  The eight warps of a CTA take eight consecutive tiles of the same frame and share one
 // prologue (axis tables + per-crop geometry) behind the CTA's single barrier.  The CTA is number cta_in_frame of the
 // CTAs working on frame b; each of its warps takes tiles_per_warp tiles.
-template <typename GT, int CG, bool EXACT>
+template <typename GT, int CG, bool EXACT, bool GRAY = false>
 __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *gx_map, const float *xs, const float *ys,
                                         const bool any_fallback, const ScatterGeom *geom, float *tiles, const float *zero_plane,
                                         const int b, const int cta_in_frame, const int tiles_per_warp)
@@ -81,7 +80,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                 __syncwarp();
                 touched = true;
             }
-            const GT *gyc = p.gray ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
+            const GT *gyc = GRAY ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
             for (int cp = 0; cp < P; ++cp)
@@ -101,7 +100,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                         float gv[CG];
                         const GT *gp = gyc + i * p.oW + j;
 #pragma unroll
-                        for (int ch = 0; ch < CG; ++ch) gv[ch] = ch < nc ? load_gy<GT>(gp, ch, npx, p.gray) : 0.f;
+                        for (int ch = 0; ch < CG; ++ch) gv[ch] = ch < nc ? load_gy<GT, GRAY>(gp, ch, npx) : 0.f;
                         ScatterTaps st;
                         if (!scatter_taps(th, xs[j], ys[i], p.H, p.W, r0, tr, s0, tw, st)) continue;
                         const Tap &t = st.t;
@@ -185,7 +184,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                 for (int e = lane; e < n4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
             }
-            gx_writeout_slow<GT, CG>(p, xs, ys, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
+            gx_writeout_slow<GT, CG, GRAY>(p, xs, ys, tile, gxb, gy, b, c0, nc, r0, tr, s0, tw, any_fallback);
         }
         __syncwarp();
     }
@@ -195,7 +194,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
 
 // Scalar write-out of a warp's tile, plus -- for crops whose transform is too degenerate for the phased scatter --
 // their contribution gathered per frame pixel (exact, slow, rare).  Out of line: keeps the fast path's registers low.
-template <typename GT, int CG>
+template <typename GT, int CG, bool GRAY>
 __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *xs, const float *ys, const float *tile,
                                               float *gxb, const GT *gy, int b, int c0, int nc,
                                               int r0, int tr, int s0, int tw, bool any_fallback)
@@ -213,9 +212,9 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
                 const Theta th = load_theta_masked(p.theta + 6 * ((size_t)b * p.K + kk), p.mask01);
                 if (make_scatter_geom(th, p.H, p.W, p.oH, p.oW).P != 0) continue;
                 const InvCrop inv = make_inv_crop(th, p.H, p.W, p.oH, p.oW);
-                const GyLoader<GT> ld = {(size_t)npx, p.gray, c0};
+                const GyLoader<GT, GRAY> ld = {(size_t)npx};
                 gather_from_crop<CG>(inv, xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
-                                     p.gray ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx,
+                                     GRAY ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx,
                                      nc, ld, acc);
             }
 #pragma unroll

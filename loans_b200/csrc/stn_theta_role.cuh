@@ -94,7 +94,7 @@ __device__ __forceinline__ void reduce_gtheta(const CropParams &p, const float (
 
 }
 
-template <typename GT, int CG, bool EXACT>
+template <typename GT, int CG, bool EXACT, bool GRAY = false>
 __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
 {
     const int C = EXACT ? CG : p.C;
@@ -106,7 +106,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * C * plane;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (p.gray ? 1 : C) * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : C) * npx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
 
@@ -135,7 +135,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch) {
                 load_taps(xb + ch * plane, a, p.W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
-                px.g[ch] = load_gy<GT>(gyb + w.q, ch, npx, p.gray);
+                px.g[ch] = load_gy<GT, GRAY>(gyb + w.q, ch, npx);
             }
         };
         auto finish = [&](const Px &px) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
             for (int ch = 0; ch < CG; ++ch)
                 if (c0 + ch < C) {
                     load_taps(xc + ch * plane, a, p.W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-                    g[ch] = load_gy<GT>(gc, ch, npx, p.gray);
+                    g[ch] = load_gy<GT, GRAY>(gc, ch, npx);
                 }
 #pragma unroll
             for (int ch = 0; ch < CG; ++ch)
