@@ -256,6 +256,8 @@ def run_ours(args):
         _lib.tma_forward(True)
     if args.no_pdl:
         _lib.pdl(False)
+    if os.environ.get("STN_THETA_ONLY_KERNEL") == "0":      # A/B: gx == NULL through the two-role kernel
+        _lib.check(L.loans_stn_configure(11, 0), "loans_stn_configure")
     if args.band != "auto":
         _lib.band_backward(args.band == "on")
     sampler = ClockSampler(local_rank)

@@ -94,7 +94,9 @@ __device__ __forceinline__ void reduce_gtheta(const CropParams &p, const float (
 
 }
 
-template <typename GT, int CG, bool EXACT, bool GRAY = false>
+// ILP2: two crop pixels in flight per thread (needs the channel count at compile time and ~80 registers: the theta-only
+// kernel of frames that take no gradient; inside the 64-register two-role kernel it measured slower)
+template <typename GT, int CG, bool EXACT, bool GRAY = false, bool ILP2 = false>
 __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
 {
     const int C = EXACT ? CG : p.C;
@@ -114,7 +116,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
 #ifndef STN_THETA_ILP
 #define STN_THETA_ILP 1      // 2 = two pixels in flight per thread: measured slower here (register pressure)
 #endif
-    if (EXACT && STN_THETA_ILP == 2) {
+    if (EXACT && (ILP2 || STN_THETA_ILP == 2)) {
         // all channels in one group: two crop pixels per thread in flight (taps and gy of both requested before
         // either is reduced), one memory round trip per pair of pixels
         struct Px {
