@@ -468,8 +468,8 @@ def run_ours(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("%s%s" % (wl.name, "" if need_gx else "_nogx"), {}).get("bwd_dram_bytes")
     # ---- the DRAM write rate of this GPU, measured here: zero-fill of the rotating gx buffers (plain torch fill kernels, a
-    # calibration like MEASURED_PEAKS.json's copy, not part of the path).  The backward is write-dominated (gx is dense) and a
-    # B200 sustains markedly fewer bytes/s of pure writes than of copy traffic, so the copy peak overstates what it can reach.
+    # calibration like MEASURED_PEAKS.json's copy, not part of the path).  The backward is write-dominated (gx is dense): this is
+    # what the same bytes cost when nothing but the stores is done, in the same graph harness, launch included.
     write_cal = None
     if need_gx:
         g_fill = capture(lambda: [e["gx"].zero_() for e in sets])

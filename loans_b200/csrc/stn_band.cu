@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     TRACE(2);
     if (!(p.band_flags & 2) && i0 < i1) {
         // every frame row segment this CTA will gather from, requested into L2 now, in one go, before any CTA has started to
-        // store: gx is bound by the DRAM write rate, and a load that queues behind a burst of stores waits for the whole burst
+        // store: a load that queues behind a burst of bulk stores waits for the whole burst (per-CTA timestamps, profiles/README.md)
         const int ua = (coltab[0].code & kAxIdxMask) - 1, ub = (coltab[oW - 1].code & kAxIdxMask);
         const int c_lo = max(ua, 0) & ~31, c_hi = min(ub, W - 1);                  // columns, 128-byte lines
         const int lines = c_hi >= c_lo ? (c_hi - c_lo) / 32 + 1 : 0;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                          (uint32_t)(sp.nrows * W * 4));
         }
         // (6) the all-zero frame rows this band owns, from the zero plane.  After the tile rows by default: gx is bound by the
-        //     DRAM write rate, and taps requested behind a burst of bulk stores wait for the whole burst to drain
+        //     taps requested behind a burst of bulk stores wait for the whole burst to drain
         if (!(p.band_flags & 1)) zero_spans();
         bulk_commit();
         pending = true;
