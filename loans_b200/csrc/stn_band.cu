@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                 bulk_s2g(gxb + (size_t)ch * fpx + (size_t)sp.row * W, tile + ch * tile_plane + sp.slot * W,
                          (uint32_t)(sp.nrows * W * 4));
         }
-        // (6) the all-zero frame rows this band owns, from the zero plane.  After the tile rows by default: gx is bound by the
-        //     taps requested behind a burst of bulk stores wait for the whole burst to drain
+        // (6) the all-zero frame rows this band owns, from the zero plane.  After the tile rows by default: taps requested
+        //     behind a burst of bulk stores wait for the whole burst to drain
         if (!(p.band_flags & 1)) zero_spans();
         bulk_commit();
         pending = true;
