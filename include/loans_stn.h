@@ -54,11 +54,13 @@ unsigned long long loans_stn_launch_count(void);
  *   measured faster at every BASELINE size (profiles/README.md).
  * LOANS_STN_CFG_FORCE_GENERAL != 0: never take an axis-aligned kernel, whatever the other switches say.
  * LOANS_STN_CFG_BAND_BACKWARD: backward of axis-aligned crops (mask01 == 0, one crop per frame, gx wanted, w % 4 == 0)
- *   through the band kernel (stn_band.cu).  -1 (default): where it measured faster (frame rows of >= 4 KiB, e.g. 512-px
- *   frames), 1: whenever it applies, 0: never.  gx, ggrid: same values; gtheta: same sums in a different order (both
+ *   through the band kernels (stn_band.cu).  -1 (default): where they measured faster (row bands: narrow frames and enough
+ *   crops to fill the machine, e.g. 64 crops of 64 rows from 224-px frames; CTA bands: frame rows of >= 4 KiB, e.g. 512-px
+ *   frames), 1: whenever they apply, 0: never.  gx, ggrid: same values; gtheta: same sums in a different order (both
  *   within the 1e-4 bar).
  * LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: tuning knobs of the band kernel for A/B measurements
- *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant); 0 = automatic.
+ *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant: 1, 2 CTA bands, 3 row bands);
+ *   0 = automatic.
  * LOANS_STN_CFG_PDL (default 1): the fused kernels (crop_fwd, crop_bwd, sampler_fwd) are launched with programmatic
  *   stream serialisation: their CTAs may become resident, and fill their shared-memory tables, while the previous kernel of
  *   the stream is still draining; they touch global memory only after griddepcontrol.wait, so stream order is preserved

@@ -37,7 +37,7 @@ int launch_sampler_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stream);
 int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
-int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not a band shape, use the general kernel
+int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement);   // -1: use the general kernel
 void band_tuning(int which, int value);
 int launch_prepare_images(const float *x, float *out, float scale, int b, int h, int w, cudaStream_t stream);      // -1: shape not supported, use the general kernel
 
@@ -94,13 +94,12 @@ static int crop_bwd_dispatch(const CropParams &p, float mask01, int k, int c, in
 {
     // mask01 == 0 (LoANs' ratio = 0.0), one crop per frame, gx wanted: the band backward -- every crop pixel evaluated
     // once, gx written once by the band that owns the frame rows (stn_band.cu); crops it declines run the general roles
-    // inside the same launch.  Measured on B200 (profiles/README.md) it wins where frame rows are wide (512-px frames:
-    // 192 vs 209 us at BASELINE config 3), ties at config 2 and loses at config 5, so by default it is taken for frame
-    // rows of at least 4 KiB per channel group; LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on / off.
+    // inside the same launch.  By default it is taken where it measured faster than the general kernel on B200 (row bands
+    // for narrow frames and enough crops, CTA bands for wide frame rows; the rule is in launch_crop_bwd_band);
+    // LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on (wherever it applies) / off.
     const int band = g_band_backward.load();
-    const bool band_shape = (long long)w * c * (long long)sizeof(float) >= 4096;
-    if (mask01 == 0.0f && k == 1 && gx != nullptr && (band == 1 || (band < 0 && band_shape)) && !g_force_general.load()) {
-        const int rc = launch_crop_bwd_band(p, gy_dtype, stream);
+    if (mask01 == 0.0f && k == 1 && gx != nullptr && band != 0 && !g_force_general.load()) {
+        const int rc = launch_crop_bwd_band(p, gy_dtype, stream, band < 0);
         if (rc >= 0) return rc;
     }
     return launch_crop_bwd(p, gy_dtype, stream);

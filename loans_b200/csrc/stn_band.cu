@@ -74,7 +74,9 @@ __device__ __noinline__ void band_declined(const CropParams &p, const Theta &th,
 }
 
 // ILP = crop pixels in flight per thread, MINB = CTAs per SM the register budget is set for
-template <typename GT, int CG, int ILP, int MINB, bool GRAY>
+// ROWBAND: every WARP works through bands of ONE crop row on a private two-row tile, synchronising with __syncwarp() only
+// (no CTA barrier between the prologue and the gtheta reduction); otherwise the CTA works through multi-row bands together.
+template <typename GT, int CG, int ILP, int MINB, bool GRAY, bool ROWBAND = false>
 __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __grid_constant__ CropParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -174,6 +176,138 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     const int nphases = P * Q;
 
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ROWBAND) {
+        // ---- one crop row per band, one warp per band.  The band of crop row a owns the frame rows from the first one row a
+        // touches to the first one row a + 1 touches; at most two of them are touched (the rest is zero), so the warp's tile is
+        // two frame rows per channel.  With P > 1 the P - 1 crop rows above are re-evaluated for the taps that land in those rows.
+        const int wrp = tid >> 5, ln = tid & 31;
+        float *wtile = tile + wrp * (CG * 2 * W);
+        const int wplane = 2 * W;
+        bool wpending = false;
+        for (int a = i0 + wrp; a < i1; a += kWarps) {
+            const BandPlan pl = plan_band(rowtab, t0, a, i1, oH, H, P, 2, 1, sm.flags[1]);
+            if (wpending) {                                          // this warp's previous tile has been read by the TMA unit
+                bulk_wait_read();
+                __syncwarp();
+            }
+            {
+                float4 *t4 = reinterpret_cast<float4 *>(wtile);
+                for (int e = ln; e < CG * wplane / 4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            for (int row = pl.h; row < pl.b; ++row) {
+                const BandAxis rw = rowtab[row - t0];
+                int s0, s1;
+                band_row_slots(pl, rw, row, s0, s1);
+                const bool own = row >= pl.a;
+                if (!own && s0 < 0 && s1 < 0) continue;                // a halo row that reaches none of this band's frame rows
+                const int v0 = rw.code & kAxIdxMask;
+                // ILP crop pixels per lane in flight: the taps and gy of all of them are requested before any is reduced
+                struct RPx {
+                    float v[CG][4], g[CG];
+                    int j;
+                    bool live;
+                };
+                auto rprepare = [&](RPx &px, int j) {
+                    px.j = j;
+                    px.live = j < oW;
+                    if (!px.live) return;
+                    const int u0 = coltab[j].code & kAxIdxMask;
+                    TapAddr ta;
+                    ta.c0 = u0 >= 1; ta.c1 = u0 <= W - 1; ta.r0 = v0 >= 1; ta.r1 = v0 <= H - 1;
+                    ta.o00 = (v0 - 1) * W + (u0 - 1);
+                    const GT *gp = gyb + row * oW + j;
+#pragma unroll
+                    for (int ch = 0; ch < CG; ++ch) {
+                        if (own) load_taps(xb + ch * plane, ta, W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
+                        px.g[ch] = load_gy<GT, GRAY>(gp, ch, npx);
+                    }
+                };
+                auto rreduce = [&](const RPx &px) {                    // gtheta sums and ggrid: the band's own row only
+                    if (!px.live || !own) return;
+                    const BandAxis col = coltab[px.j];
+                    const Tap t = tap_from_band_axes(col, rw, H, W);
+                    float su = 0.f, sv = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < CG; ++ch) {
+                        float gu, gv;
+                        grad_uv(t, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3], gu, gv);
+                        gu = f_mul(gu, px.g[ch]);
+                        gv = f_mul(gv, px.g[ch]);
+                        if (ch == 0) { su = gu; sv = gv; }
+                        else { su = f_add(su, gu); sv = f_add(sv, gv); }
+                    }
+                    finish_grad_uv(t, H, W, su, sv);
+                    const int qq = row * oW + px.j;
+                    if (ggo) {
+                        ggo[qq] = su;
+                        ggo[npx + qq] = sv;
+                    }
+                    if (ggu) {
+                        su = f_add(su, __ldg(ggu + qq));
+                        sv = f_add(sv, __ldg(ggu + npx + qq));
+                    }
+                    s[0] = fmaf(su, col.lin, s[0]); s[1] = fmaf(su, rw.lin, s[1]); s[2] += su;
+                    s[3] = fmaf(sv, col.lin, s[3]); s[4] = fmaf(sv, rw.lin, s[4]); s[5] += sv;
+                };
+                auto rscatter = [&](const RPx &px) {                   // gy * wu * wv into the warp's tile
+                    const BandAxis col = coltab[px.j];
+                    const bool c0 = (col.code & kAxTap0) != 0, c1 = (col.code & kAxTap1) != 0;
+                    float *tp = wtile + ((col.code & kAxIdxMask) - 1);
+                    float *r0p = tp + s0 * W, *r1p = tp + s1 * W;
+#pragma unroll
+                    for (int ch = 0; ch < CG; ++ch) {
+                        const float a1 = f_mul(px.g[ch], col.w1), a0 = f_mul(px.g[ch], col.w0);
+                        if (s0 >= 0) {
+                            if (c0) r0p[ch * wplane] = f_add(r0p[ch * wplane], f_mul(a1, rw.w1));
+                            if (c1) r0p[ch * wplane + 1] = f_add(r0p[ch * wplane + 1], f_mul(a0, rw.w1));
+                        }
+                        if (s1 >= 0) {
+                            if (c0) r1p[ch * wplane] = f_add(r1p[ch * wplane], f_mul(a1, rw.w0));
+                            if (c1) r1p[ch * wplane + 1] = f_add(r1p[ch * wplane + 1], f_mul(a0, rw.w0));
+                        }
+                    }
+                };
+                const bool touches = s0 >= 0 || s1 >= 0;
+                for (int j0 = 0; j0 < oW; j0 += 32 * ILP) {
+                    RPx px[ILP];
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) rprepare(px[u], j0 + 32 * u + ln);
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) rreduce(px[u]);
+                    // crop pixels of one column phase never share a frame pixel (lanes of one chunk are 32 columns apart from the next)
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) {
+                        for (int cq = 0; cq < Q; ++cq) {
+                            if (px[u].live && touches && (Q == 1 || px[u].j % Q == cq)) rscatter(px[u]);
+                            if (Q > 1) __syncwarp();
+                        }
+                        if (ILP > 1) __syncwarp();                      // chunk boundary: neighbouring columns meet at lanes 31 | 0
+                    }
+                }
+                __syncwarp();                                          // rows are worked through one after the other
+            }
+            // tile rows and the zero rows around them -> gx, one bulk copy per lane
+            fence_async_smem();
+            __syncwarp();
+            {
+                const int nspans = band_span_count(pl);
+                if (ln < nspans * CG) {
+                    const int t = ln / CG, ch = ln - t * CG;
+                    const BandSpan sp = band_span(pl, rowtab, t0, H, t);
+                    float *dst = gxb + (size_t)ch * fpx + (size_t)sp.row * W;
+                    if (sp.slot >= 0) {
+                        if (sp.nrows > 0) bulk_s2g(dst, wtile + ch * wplane + sp.slot * W, (uint32_t)(sp.nrows * W * 4));
+                    } else {
+                        for (int r = 0; r < sp.nrows; r += zrows)
+                            bulk_s2g(dst + (size_t)r * W, zero_plane, (uint32_t)(min(zrows, sp.nrows - r) * W * 4));
+                    }
+                }
+                bulk_commit();
+            }
+            wpending = true;
+        }
+    }
     const int warp = tid >> 5, lane = tid & 31;
     bool pending = false;                                             // tile stores of the previous band in flight
     struct Px {
@@ -181,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         int i, j;
         bool live;
     };
-    for (int a = i0; a < i1;) {
+    for (int a = i0; !ROWBAND && a < i1;) {
         const BandPlan pl = plan_band(rowtab, t0, a, i1, oH, H, P, p.band_cap, p.band_rows, sm.flags[1]);
         const int nspans = band_span_count(pl);
         const int npxb = (pl.b - pl.h) * oW;
@@ -364,13 +498,13 @@ void band_tuning(int which, int value)
     else g_band_variant = value;
 }
 
-template <typename GT, int CG, int ILP, int MINB, bool GRAY = false>
+template <typename GT, int CG, int ILP, int MINB, bool GRAY = false, bool ROWBAND = false>
 static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
     if (smem > 48 * 1024) {
         static size_t granted = 0;
         if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY, ROWBAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             granted = smem;
         }
@@ -383,25 +517,33 @@ static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned 
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, cs);
-    return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY>, p);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY, ROWBAND>, p);
 }
 
+// kind 1: CTA bands, one crop pixel in flight per thread, 64 registers, four CTAs per SM; kind 2: CTA bands, two pixels in
+// flight, 80 registers, three CTAs per SM (kept for A/B runs: never faster); kind 3: row bands (one crop row per warp)
 template <typename GT, int CG>
-static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s, int kind)
 {
-    // variant 0 (default): one crop pixel in flight per thread, 64 registers, four CTAs per SM -- the fastest at every
-    // measured shape; variant 1: two pixels in flight, 80 registers, three CTAs per SM (kept for A/B runs)
     if constexpr (CG == 3) {
-        if (p.gray) return launch_band_ttt<GT, 3, 1, 4, true>(p, ctas, cs, smem, s);   // grayscale epilogue: its own kernel
+        if (p.gray)                                                    // grayscale epilogue: its own kernel instances
+            return kind == 3 ? launch_band_ttt<GT, 3, 1, 4, true, true>(p, ctas, cs, smem, s)
+                             : launch_band_ttt<GT, 3, 1, 4, true, false>(p, ctas, cs, smem, s);
     }
-    switch (g_band_variant & 15) {
-    case 1: return launch_band_ttt<GT, CG, 2, 3>(p, ctas, cs, smem, s);
+    switch (kind) {
+    case 3: return launch_band_ttt<GT, CG, 1, 4, false, true>(p, ctas, cs, smem, s);
+    case 2: return launch_band_ttt<GT, CG, 2, 3>(p, ctas, cs, smem, s);
     default: return launch_band_ttt<GT, CG, 1, 4>(p, ctas, cs, smem, s);
     }
 }
 
-// Returns -1 when the shape is not one the band kernel takes (the caller then launches the general kernel).
-int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream)
+// Returns -1 when the shape is not one the band kernels take -- or, with by_measurement, not one where they measured faster
+// than the general kernel (profiles/README.md) -- and the caller then launches the general kernel.
+//   row bands: narrow frames (eight two-row tiles fit the shared-memory budget) and enough crops to fill the machine --
+//     they win from 64 crops of 64 rows (16.7 vs 20.9 us) and from ~256 crops of 75 rows (77.9 vs 82.6 us; 253 vs 262 us
+//     at 1024), lose below (a warp works through its rows and 32-pixel chunks one memory round trip after the other);
+//   CTA bands: frame rows of at least 4 KiB (512-px RGB frames: 192 vs 209-214 us at BASELINE config 3).
+int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement)
 {
     if (!p.gx || p.K != 1 || p.mask01 != 0.0f) return -1;
     if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
@@ -419,6 +561,37 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream)
     // CTAs per crop (= cluster size): 8 while that leaves every CTA at least one crop row
     unsigned cs = g_band_cs > 0 ? (unsigned)g_band_cs : 8;
     while (cs > 1 && (int)cs > p.oH) cs >>= 1;
+    // row bands: a CTA's eight warps take eight crop rows at a time -- the cluster size (any size up to 8) that leaves the
+    // fewest warps idle in the last pass, the largest one among equals
+    unsigned cs_row = cs;
+    if (g_band_cs == 0) {
+        double best = 0.0;
+        for (unsigned c = 1; c <= 8 && (int)c <= p.oH; ++c) {
+            const int rows = (p.oH + (int)c - 1) / (int)c;
+            const double util = (double)p.oH / ((double)c * kWarps * ((rows + kWarps - 1) / kWarps));
+            if (util >= best * 0.999) { if (util > best) best = util; cs_row = c; }
+        }
+    }
+    const bool fits_row = budget >= (size_t)p.band_zero_bytes + 2 * kWarps * slot_bytes;
+    const int knob = g_band_variant & 15;                               // 0: automatic; 1, 2: CTA bands; 3: row bands
+    bool rowband;
+    if (knob == 3) {
+        if (!fits_row) return -1;
+        rowband = true;
+    } else if (knob == 1 || knob == 2) {
+        rowband = false;
+    } else {
+        rowband = fits_row;
+        if (by_measurement) {
+            if (p.gray) rowband = false;             // behind the grayscale epilogue the general kernel measured faster (295 vs 336 us at cfg5)
+            if (rowband) {
+                const int passes = (((p.oH + (int)cs_row - 1) / (int)cs_row) + kWarps - 1) / kWarps, chunks = (p.oW + 31) / 32;
+                if ((long long)p.N * cs_row < 256LL * passes * chunks) rowband = false;
+            }
+            if (!rowband && slot_bytes < 4096) return -1;
+        }
+    }
+    if (rowband) cs = cs_row;
     p.ctas_per_crop = (int)cs;
     p.px_per_cta = (int)(((long long)p.oH * p.oW + cs - 1) / cs);     // declined crops: theta role share
     p.band_rows_cta = (p.oH + (int)cs - 1) / (int)cs;
@@ -432,6 +605,11 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream)
     {
         const int need = (22 * (p.band_rows - 1) + 9) / 10 + 3 > 2 * p.band_rows ? (22 * (p.band_rows - 1) + 9) / 10 + 3 : 2 * p.band_rows;
         p.band_cap = need < cap_max ? need : cap_max;
+    }
+    if (rowband) {
+        // row bands: eight warp-private tiles of two frame rows each
+        p.band_rows = 1;
+        p.band_cap = 2 * kWarps;                                       // rows of the whole tile region (two per warp)
     }
     p.band_flags = g_band_variant >> 4;
     p.band_tab_rows = p.band_rows_cta + kBandMaxHalo + 1;
@@ -455,15 +633,16 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream)
     if (smem > 200 * 1024) return -1;
     const long long ctas = (long long)p.N * cs;
     if (ctas > 0x7fffffffLL) return -1;
+    const int kind = rowband ? 3 : (knob == 2 ? 2 : 1);
     cudaError_t e;
     if (gy_dtype == 0)
-        e = p.C == 1 ? launch_band_tt<float, 1>(p, (unsigned)ctas, cs, smem, stream)
-          : p.C == 3 ? launch_band_tt<float, 3>(p, (unsigned)ctas, cs, smem, stream)
-                     : launch_band_tt<float, 4>(p, (unsigned)ctas, cs, smem, stream);
+        e = p.C == 1 ? launch_band_tt<float, 1>(p, (unsigned)ctas, cs, smem, stream, kind)
+          : p.C == 3 ? launch_band_tt<float, 3>(p, (unsigned)ctas, cs, smem, stream, kind)
+                     : launch_band_tt<float, 4>(p, (unsigned)ctas, cs, smem, stream, kind);
     else
-        e = p.C == 1 ? launch_band_tt<__nv_bfloat16, 1>(p, (unsigned)ctas, cs, smem, stream)
-          : p.C == 3 ? launch_band_tt<__nv_bfloat16, 3>(p, (unsigned)ctas, cs, smem, stream)
-                     : launch_band_tt<__nv_bfloat16, 4>(p, (unsigned)ctas, cs, smem, stream);
+        e = p.C == 1 ? launch_band_tt<__nv_bfloat16, 1>(p, (unsigned)ctas, cs, smem, stream, kind)
+          : p.C == 3 ? launch_band_tt<__nv_bfloat16, 3>(p, (unsigned)ctas, cs, smem, stream, kind)
+                     : launch_band_tt<__nv_bfloat16, 4>(p, (unsigned)ctas, cs, smem, stream, kind);
     count_launch();
     if (e != cudaSuccess) return set_error("crop_bwd (band) launch failed: %s", cudaGetErrorString(e));
     return 0;

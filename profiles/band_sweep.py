@@ -47,6 +47,8 @@ def main():
     dev = torch.device("cuda", 0)
     for name in names:
         wl = W.WORKLOADS[name]._replace(rotation_ratio=0.0)
+        if os.environ.get("BATCH"):
+            wl = wl._replace(batch=int(os.environ["BATCH"]))
         B, K, C, H, Wd, oH, oW = wl.batch, wl.crops_per_frame, wl.channels, wl.height, wl.width, wl.out_h, wl.out_w
         N = B * K
         ydt = torch.bfloat16 if wl.out_dtype == "bf16" else torch.float32
@@ -59,18 +61,18 @@ def main():
                          "gy": torch.from_numpy(d["gy"]).to(dev).to(ydt),
                          "gtheta": torch.empty((N, 2, 3), dtype=torch.float32, device=dev),
                          "gx": torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)})
-        reps = 40 if name == "cfg2" else 8
+        reps = 40 if wl.batch * wl.height <= 64 * 224 else 8
         _, bwd_bytes = W.algorithmic_bytes(wl, need_gx=True)
         _lib.band_backward(False)
         for tpw in [int(v) for v in os.environ.get("SWEEP_TPW", "0").split(",")]:
             _lib.check(_lib.lib().loans_stn_configure(10, tpw), "cfg")
             us = time_bwd(wl, sets, reps)
-            print(json.dumps({"wl": name, "kernel": "general", "tiles_per_warp": tpw, "us": round(us, 2), "gbs": round(bwd_bytes / us / 1e3, 1)}), flush=True)
+            print(json.dumps({"wl": name, "batch": wl.batch, "kernel": "general", "tiles_per_warp": tpw, "us": round(us, 2), "gbs": round(bwd_bytes / us / 1e3, 1)}), flush=True)
         _lib.check(_lib.lib().loans_stn_configure(10, 0), "cfg")
         _lib.band_backward(True)
         if os.environ.get("SWEEP", "x") == "":
             continue
-        combos = os.environ.get("SWEEP", "0,1,2;8;0;0;0,1,2,3").split(";")
+        combos = os.environ.get("SWEEP", "1,3;0;0;0;0").split(";")
         variants, css, tiles, rowss, flagss = [[int(v) for v in c.split(",")] for c in combos]
         for variant0 in variants:
           for flags in flagss:
@@ -80,7 +82,7 @@ def main():
                     for rows in rowss:
                         _lib.band_tuning(cs=cs, rows=rows, tile_kb=tile_kb, variant=variant)
                         us = time_bwd(wl, sets, reps)
-                        print(json.dumps({"wl": name, "kernel": "band", "variant": variant, "cs": cs, "tile_kb": tile_kb,
+                        print(json.dumps({"wl": name, "batch": wl.batch, "kernel": "band", "variant": variant, "cs": cs, "tile_kb": tile_kb,
                                           "rows": rows, "us": round(us, 2), "gbs": round(bwd_bytes / us / 1e3, 1)}), flush=True)
         _lib.band_tuning()
         _lib.band_backward(None)

@@ -253,7 +253,7 @@ BAND_THETAS = np.array([
 ], np.float32)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])      # automatic, CTA bands (1, 2 pixels in flight), row bands
 @pytest.mark.parametrize("shape", [(3, 24, 24, 9, 9), (3, 17, 32, 12, 7), (1, 8, 8, 16, 16), (3, 20, 12, 1, 5),
                                    (4, 13, 8, 6, 1), (3, 64, 48, 5, 33), (3, 40, 40, 37, 3), (3, 96, 128, 75, 75)])
 def test_band_backward_hard_boxes(G, shape, variant):
@@ -266,10 +266,10 @@ def test_band_backward_hard_boxes(G, shape, variant):
     try:
         _lib.band_backward(True)
         n0 = _lib.launch_count()
-        for cs, rows in ((0, 0), (1, 1), (2, 3), (4, 0)):
+        for cs, rows in ((0, 0), (1, 1), (2, 3), (4, 0), (5, 0)):
             _lib.band_tuning(cs=cs, rows=rows, variant=variant)
             _full_check(G, x, BAND_THETAS, (oh, ow), 0.0, 1, seed=11)
-        assert _lib.launch_count() - n0 == 8            # one forward + one backward launch per check
+        assert _lib.launch_count() - n0 == 10           # one forward + one backward launch per check
     finally:
         _lib.band_tuning()
         _lib.band_backward(None)

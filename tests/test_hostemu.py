@@ -176,7 +176,7 @@ def run_band(lib, x, theta, osz, gy, gg, mask, cs, cap, max_rows=1 << 20):
     return gt, gx, ggo, ok.astype(bool), conflicts, list(stats)
 
 
-def check_band(lib, x, theta, osz, mask=0.0, seed=0, expect_ok=None, layouts=((1, 4), (2, 6, 2), (3, 16), (8, 19), (5, 7, 1))):
+def check_band(lib, x, theta, osz, mask=0.0, seed=0, expect_ok=None, layouts=((1, 4), (2, 6, 2), (3, 16), (8, 19), (5, 7, 1), (8, 2, 1))):
     rng = np.random.default_rng(seed)
     n, c = theta.shape[0], x.shape[1]
     gy = rng.standard_normal((n, c) + tuple(osz), dtype=np.float32)
@@ -209,7 +209,7 @@ def check_band(lib, x, theta, osz, mask=0.0, seed=0, expect_ok=None, layouts=((1
 def test_band_backward_on_workload_shapes(emu, wl, batch):
     wl = W.WORKLOADS[wl]
     d = W.make_inputs(wl, batch=batch, rotate=True)
-    ok = check_band(emu, d["x"], d["theta"], (wl.out_h, wl.out_w), 0.0, layouts=((8, 16), (8, 18), (4, 12), (1, 6)))
+    ok = check_band(emu, d["x"], d["theta"], (wl.out_h, wl.out_w), 0.0, layouts=((8, 16), (8, 18), (4, 12), (1, 6), (8, 2, 1)))
     assert ok is not None and ok.all()            # every synthetic LoANs crop is a down-sampling, upright box
 
 
