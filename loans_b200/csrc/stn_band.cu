@@ -121,40 +121,46 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         }
     }
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
-    const BandCrop bc = make_band_crop(th, p.H, p.W, p.oH, p.oW);     // the same verdict in every CTA of the cluster
-    if (!bc.ok) {
-        band_declined<GT, CG, GRAY>(p, th, smem_raw, sm, xs, ys, geom, n, rank);
-        return;
-    }
     TRACE(1);
     const int H = p.H, W = p.W, oH = p.oH, oW = p.oW;
-    const int P = bc.P, Q = bc.Q;
     const int i0 = rank * p.band_rows_cta, i1 = min(oH, i0 + p.band_rows_cta);
-    const int t0 = max(i0 - (P - 1), 0), t1 = min(i1 + 1, oH);
-    // ---- prologue: coordinate chains once per crop column / row, zero plane
-    for (int k = tid; k < oW; k += kThreads) coltab[k] = make_band_axis(th.t00, th.t01, th.t02, lin_x_at(p, k), true, W);
-    for (int k = tid; k < t1 - t0; k += kThreads)
-        rowtab[k] = make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, t0 + k), false, H);
-    if (tid >= kThreads - 2) {                                        // first and last frame row the crop touches: L, E
-        const int last = tid == kThreads - 1;
-        int lo, hi;
-        band_row_range(make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, last ? oH - 1 : 0), false, H), H, lo, hi);
-        sm.flags[last] = last ? hi : lo;
+    const int t0 = max(i0 - kBandMaxHalo, 0), t1 = min(i1 + 1, oH);   // rows tabulated: the longest halo the plan can ask for
+    // ---- prologue: the crop's verdict (one warp), coordinate chains once per crop column / row (the others)
+    if (tid >= kThreads - 32) {
+        const BandCrop v = make_band_crop(th, H, W, oH, oW);              // the same in every CTA of the cluster
+        if (tid == kThreads - 32) { sm.bc[0] = v.ok; sm.bc[1] = v.P; sm.bc[2] = v.Q; }
+        if (tid >= kThreads - 2) {                                        // first and last frame row the crop touches: L, E
+            const int last = tid == kThreads - 1;
+            int lo, hi;
+            band_row_range(make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, last ? oH - 1 : 0), false, H), H, lo, hi);
+            sm.flags[last] = last ? hi : lo;
+        }
+    } else {
+        for (int k = tid; k < oW + (t1 - t0); k += kThreads - 32) {
+            if (k < oW) coltab[k] = make_band_axis(th.t00, th.t01, th.t02, lin_x_at(p, k), true, W);
+            else rowtab[k - oW] = make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, t0 + k - oW), false, H);
+        }
     }
     __syncthreads();
     TRACE(2);
-    if (!(p.band_flags & 2) && i0 < i1) {
+    if (!sm.bc[0]) {
+        band_declined<GT, CG, GRAY>(p, th, smem_raw, sm, xs, ys, geom, n, rank);
+        return;
+    }
+    const int P = sm.bc[1], Q = sm.bc[2];
+    if (!ROWBAND && !(p.band_flags & 2) && i0 < i1) {
         // every frame row segment this CTA will gather from, requested into L2 now, in one go, before any CTA has started to
         // store: a load that queues behind a burst of bulk stores waits for the whole burst (per-CTA timestamps, profiles/README.md)
         const int ua = (coltab[0].code & kAxIdxMask) - 1, ub = (coltab[oW - 1].code & kAxIdxMask);
         const int c_lo = max(ua, 0) & ~31, c_hi = min(ub, W - 1);                  // columns, 128-byte lines
         const int lines = c_hi >= c_lo ? (c_hi - c_lo) / 32 + 1 : 0;
-        const int nrow2 = 2 * (i1 - t0);                                            // two tap rows per crop row (halo included)
+        const int h0 = max(i0 - (P - 1), 0);                                        // first row evaluated (halo included)
+        const int nrow2 = 2 * (i1 - h0);                                            // two tap rows per crop row
         const float *xn = p.x + (size_t)n * CG * ((size_t)H * W);
         for (int e = tid; e < nrow2 * lines * CG; e += kThreads) {
             const int l = e % lines, rc = e / lines;
             const int ch = rc % CG, r2 = rc / CG;
-            const int fr = (rowtab[r2 >> 1].code & kAxIdxMask) - 1 + (r2 & 1);
+            const int fr = (rowtab[h0 - t0 + (r2 >> 1)].code & kAxIdxMask) - 1 + (r2 & 1);
             if (fr >= 0 && fr < H) {
                 const float *a = xn + (size_t)ch * H * W + (size_t)fr * W + c_lo + 32 * l;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
@@ -190,11 +196,8 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                 bulk_wait_read();
                 __syncwarp();
             }
-            {
-                float4 *t4 = reinterpret_cast<float4 *>(wtile);
-                for (int e = ln; e < CG * wplane / 4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            __syncwarp();
+            bool need_zero = true;                                   // the tile is zeroed while the first loads are in flight
+            TRACE(4);
             for (int row = pl.h; row < pl.b; ++row) {
                 const BandAxis rw = rowtab[row - t0];
                 int s0, s1;
@@ -273,8 +276,16 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                     RPx px[ILP];
 #pragma unroll
                     for (int u = 0; u < ILP; ++u) rprepare(px[u], j0 + 32 * u + ln);
+                    if (need_zero) {
+                        float4 *t4 = reinterpret_cast<float4 *>(wtile);
+                        for (int e = ln; e < CG * wplane / 4; e += 32) t4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncwarp();
+                        need_zero = false;
+                    }
+                    TRACE(5);
 #pragma unroll
                     for (int u = 0; u < ILP; ++u) rreduce(px[u]);
+                    TRACE(6);
                     // crop pixels of one column phase never share a frame pixel (lanes of one chunk are 32 columns apart from the next)
 #pragma unroll
                     for (int u = 0; u < ILP; ++u) {
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                 __syncwarp();                                          // rows are worked through one after the other
             }
             // tile rows and the zero rows around them -> gx, one bulk copy per lane
+            TRACE(7);
             fence_async_smem();
             __syncwarp();
             {
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                 bulk_commit();
             }
             wpending = true;
+            TRACE(9);
         }
     }
     const int warp = tid >> 5, lane = tid & 31;
@@ -540,8 +553,9 @@ static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned c
 // Returns -1 when the shape is not one the band kernels take -- or, with by_measurement, not one where they measured faster
 // than the general kernel (profiles/README.md) -- and the caller then launches the general kernel.
 //   row bands: narrow frames (eight two-row tiles fit the shared-memory budget) and enough crops to fill the machine --
-//     they win from 64 crops of 64 rows (16.7 vs 20.9 us) and from ~256 crops of 75 rows (77.9 vs 82.6 us; 253 vs 262 us
-//     at 1024), lose below (a warp works through its rows and 32-pixel chunks one memory round trip after the other);
+//     they win from 64 crops of 64x64 (16.1 vs 20.9 us; 30 vs 36 us at 128, 56 vs 67 us at 256) and from 256 crops of 75x75
+//     (74 vs 83 us; 241 vs 262 us at 1024), lose below (12.4 vs 13.7 us at 32 crops of 64x64, 44 vs 48 us at 128 crops of
+//     75x75): a warp works through its rows and 32-pixel chunks one memory round trip after the other;
 //   CTA bands: frame rows of at least 4 KiB (512-px RGB frames: 192 vs 209-214 us at BASELINE config 3).
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement)
 {
@@ -586,7 +600,7 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool b
             if (p.gray) rowband = false;             // behind the grayscale epilogue the general kernel measured faster (295 vs 336 us at cfg5)
             if (rowband) {
                 const int passes = (((p.oH + (int)cs_row - 1) / (int)cs_row) + kWarps - 1) / kWarps, chunks = (p.oW + 31) / 32;
-                if ((long long)p.N * cs_row < 256LL * passes * chunks) rowband = false;
+                if ((long long)p.N * cs_row < 200LL * passes * chunks) rowband = false;
             }
             if (!rowband && slot_bytes < 4096) return -1;
         }

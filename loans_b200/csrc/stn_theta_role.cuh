@@ -39,6 +39,7 @@ struct BwdSmem {
     float red[kWarps][6];
     float part[6];        // this CTA's partial gtheta sums, read by cluster rank 0 through DSMEM
     int flags[2];
+    int bc[4];            // band kernels: the crop's verdict (ok, P, Q), computed once per CTA
 };
 
 // The six per-thread partial sums of gtheta -> gtheta[n]: warp shuffles, shared memory, then cluster rank 0 adds the

@@ -6,5 +6,5 @@ for extra in "$@"; do
   make -C loans_b200/csrc clean >/dev/null 2>&1
   make -C loans_b200/csrc -j8 EXTRA="$extra" >/dev/null 2>&1 || { echo "[$extra] build failed"; continue; }
   echo "== EXTRA=[$extra]"
-  SWEEP="" timeout 300 python profiles/band_sweep.py $wls 2>&1 | tail -8
+  SWEEP="${AB_SWEEP:-}" timeout 300 python profiles/band_sweep.py $wls 2>&1 | tail -${AB_TAIL:-8}
 done

@@ -24,6 +24,7 @@ gt = torch.empty((N, 2, 3), dtype=torch.float32, device=dev)
 gx = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 _lib.band_tuning(variant=a[0], cs=a[1], rows=a[2], tile_kb=a[3])
+_lib.band_backward(True)
 cs = a[1] or 8
 L = _lib.lib()
 trace = torch.zeros((N * cs, 16), dtype=torch.int64, device=dev)
