@@ -488,7 +488,7 @@ def run_ours(args):
     ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9
     ach_f = fwd_bytes / (ms_f * 1e-3) / 1e9
     ach_s = (fwd_bytes + bwd_bytes) / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "backward launch: stn_bwd_kernel (gx role + cluster-reduced theta role), or stn_bwd_band_kernel where the band backward is taken (mask01 == 0, wide frame rows)",
+    roofline = {"bound": "hbm", "kernel": "backward launch: stn_bwd_band_kernel (row bands or CTA bands) where the band backward is taken (mask01 == 0, one crop per frame; rule in launch_crop_bwd_band), else stn_bwd_kernel (gx role + cluster-reduced theta role)",
                 "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_us": ms_b * 1e3,
                 "write_bound": write_cal,

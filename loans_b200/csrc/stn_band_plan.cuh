@@ -188,8 +188,8 @@ STN_HD void band_row_slots(const BandPlan &pl, const BandAxis &row, int i, int &
 // CTA `rank` zero-fills rows [r0a, r0a + na) and [r0b, r0b + nb).  L = lo of crop row 0, E = hi of the last crop row.
 STN_HD void band_edge_rows(int L, int E, int H, int rank, int cs, int &r0a, int &na, int &r0b, int &nb)
 {
-    const long long Z = (long long)L + (long long)(H - E);
-    const int z0 = (int)(Z * rank / cs), z1 = (int)(Z * (rank + 1) / cs);
+    const int Z = L + (H - E);                       // <= H < 2^24 and cs <= 16: the products below fit 32 bits
+    const int z0 = Z * rank / cs, z1 = Z * (rank + 1) / cs;
     const int a1 = z1 < L ? z1 : L;
     r0a = z0; na = a1 - z0 > 0 ? a1 - z0 : 0;
     const int b0 = z0 > L ? z0 : L;

@@ -19,4 +19,6 @@ for k in stn_fwd_kernel stn_bwd_kernel prepare_images_kernel; do
 done
 timeout 400 ncu --set full --clock-control none --import-source on --kernel-name regex:stn_bwd_band --launch-skip 2 -c 1 -f -o $O/r1_stn_bwd_band_cfg3 \
   python profiles/run_bwd_once.py cfg3 > $O/ncu_band_cfg3.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --kernel-name regex:stn_bwd_band --launch-skip 2 -c 1 -f -o $O/r1_stn_bwd_rowband_cfg2 \
+  python profiles/run_bwd_once.py cfg2 > $O/ncu_rowband_cfg2.log 2>&1
 ls -la $O | tail -20
