@@ -104,10 +104,13 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         for (int e = threadIdx.x; e < p.band_zero_bytes / 16; e += kThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_async_smem();
     }
-    pdl_wait();
     const int cs = p.ctas_per_crop;
     const int n = blockIdx.x / cs, rank = blockIdx.x - n * cs;
     const int tid = threadIdx.x;
+#ifndef STN_BAND_PULL_REDUCE
+    push_reduce_init(sm, rank, cs);                                   // shared memory only: before the wait
+#endif
+    pdl_wait();
     {   // this CTA's gy rows do not depend on theta: start them towards L2 while theta is on its way
         const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
         const int row_elems = max(r1 - r0, 0) * p.oW;
@@ -487,7 +490,11 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         }
         bulk_commit();
     }
+#ifndef STN_BAND_PULL_REDUCE
+    reduce_gtheta_push(p, s, sm, n, rank, cs);
+#else
     reduce_gtheta(p, s, sm, n, rank, cs);
+#endif
     TRACE(10);
     bulk_wait_read();
     TRACE(11);

@@ -35,11 +35,15 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-struct BwdSmem {
+struct alignas(16) BwdSmem {
     float red[kWarps][6];
     float part[6];        // this CTA's partial gtheta sums, read by cluster rank 0 through DSMEM
     int flags[2];
     int bc[4];            // band kernels: the crop's verdict (ok, P, Q), computed once per CTA
+    // push-model reduction (band kernels): the peers of a cluster store their partials into rank 0's peer[] over DSMEM
+    // and arrive on rank 0's mbarrier; only rank 0 waits
+    unsigned long long bar;
+    float peer[8][6];
 };
 
 // The six per-thread partial sums of gtheta -> gtheta[n]: warp shuffles, shared memory, then cluster rank 0 adds the
@@ -97,6 +101,66 @@ __device__ __forceinline__ void reduce_gtheta(const CropParams &p, const float (
 
 // ILP2: two crop pixels in flight per thread (needs the channel count at compile time and ~80 registers: the theta-only
 // kernel of frames that take no gradient; inside the 64-register two-role kernel it measured slower)
+// ---- push-model reduction.  reduce_gtheta() makes every CTA of the cluster wait twice for all its peers (rank 0 PULLS the
+// partials, so the peers' shared memory has to stay alive); in a kernel of many waves that wait holds SM slots.  Here the
+// peers PUSH: six threads each store one partial sum into rank 0's shared memory (st.shared::cluster) and arrive on rank 0's
+// mbarrier with release semantics at cluster scope, then the CTA is done; rank 0 alone waits (acquire).  Nobody touches a
+// peer's shared memory, so peers may exit at once.  push_reduce_init() must run at kernel entry in every CTA of the cluster.
+__device__ __forceinline__ void push_reduce_init(BwdSmem &sm, int rank, int cs)
+{
+    if (cs <= 1) return;
+    if (rank == 0 && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.bar)), "r"(6 * (cs - 1)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cooperative_groups::this_cluster().sync();            // the barrier exists before any peer can arrive on it
+}
+
+__device__ __forceinline__ void reduce_gtheta_push(const CropParams &p, const float (&s)[6], BwdSmem &sm, int n, int rank, int cs)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float r = warp_sum(s[k]);
+        if (lane == 0) sm.red[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 6) return;
+    float tot = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kWarps; ++wi) tot += sm.red[wi][threadIdx.x];
+    if (cs > 1 && rank != 0) {
+        unsigned dst, bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(dst) : "r"((unsigned)__cvta_generic_to_shared(&sm.peer[rank][threadIdx.x])));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(bar) : "r"((unsigned)__cvta_generic_to_shared(&sm.bar)));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(tot) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+        return;
+    }
+    if (cs > 1) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+        for (int r = 1; r < cs; ++r) tot += sm.peer[r][threadIdx.x];                  // fixed order: deterministic
+    }
+    if (p.gcorners) {                                                                   // see reduce_gtheta
+        const float *gc = p.gcorners + 8 * (size_t)n + 4 * (threadIdx.x / 3);
+        const int m = threadIdx.x % 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ci = q >> 1, cj = q & 1;
+            const float w = m == 0 ? lin_x_at(p, cj ? p.oW - 1 : 0) : (m == 1 ? lin_y_at(p, ci ? p.oH - 1 : 0) : 1.0f);
+            acc = fmaf(__ldg(gc + q), w, acc);
+        }
+        tot += acc;
+    }
+    if (threadIdx.x == 1 || threadIdx.x == 3) tot = f_mul(tot, p.mask01);
+    p.gtheta[6 * (size_t)n + threadIdx.x] = tot;
+}
+
 template <typename GT, int CG, bool EXACT, bool GRAY = false, bool ILP2 = false>
 __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs, const float *ys, BwdSmem &sm, int cta)
 {
