@@ -75,6 +75,7 @@ unsigned long long loans_stn_launch_count(void);
 #define LOANS_STN_CFG_PDL 8
 #define LOANS_STN_CFG_GX_TILES_PER_WARP 10   /* general backward: frame tiles per warp of the gx role, 0 = automatic (A/B) */
 #define LOANS_STN_CFG_THETA_ONLY_KERNEL 11 /* gx == NULL: the theta-only kernel (default 1); 0: the two-role kernel without gx CTAs (A/B) */
+#define LOANS_STN_CFG_FWD_PX_PER_CTA 12    /* forward: crop pixels per CTA (rounded up to 256); 0 = automatic (A/B) */
 #define LOANS_STN_CFG_THETA_FIRST 9   /* general backward: schedule the theta-role CTAs before the gx-role CTAs (A/B) */
 int loans_stn_configure(int key, int value);
 

@@ -49,6 +49,8 @@ static std::atomic<int> g_theta_first{0};
 bool theta_first_enabled() { return g_theta_first.load() != 0; }
 static std::atomic<int> g_gx_tpw{0};
 int gx_tiles_per_warp_override() { return g_gx_tpw.load(); }
+static std::atomic<int> g_fwd_px{0};
+int fwd_px_per_cta_override() { return g_fwd_px.load(); }
 static std::atomic<int> g_theta_only{1};
 bool theta_only_kernel_enabled() { return g_theta_only.load() != 0; }
 static std::atomic<int> g_band_backward{-1};    // -1: by shape (wide frame rows), 0: never, 1: whenever it applies
@@ -128,6 +130,7 @@ int loans_stn_configure(int key, int value)
     if (key == LOANS_STN_CFG_TMA_FORWARD) { g_tma_forward.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_GX_TILES_PER_WARP) { g_gx_tpw.store(value < 0 ? 0 : (value > 64 ? 64 : value)); return 0; }
     if (key == LOANS_STN_CFG_THETA_ONLY_KERNEL) { g_theta_only.store(value != 0); return 0; }
+    if (key == LOANS_STN_CFG_FWD_PX_PER_CTA) { g_fwd_px.store(value > 0 ? ((value + 255) / 256) * 256 : 0); return 0; }
     if (key == LOANS_STN_CFG_THETA_FIRST) { g_theta_first.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_PDL) { g_pdl.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_BAND_BACKWARD) { g_band_backward.store(value < 0 ? -1 : (value != 0)); return 0; }

@@ -124,6 +124,7 @@ int check_launch(const char *what);
 bool pdl_enabled();
 bool theta_first_enabled();
 int gx_tiles_per_warp_override();
+int fwd_px_per_cta_override();
 bool theta_only_kernel_enabled();
 // fills the launch attributes shared by the fused kernels: [cluster dimension,] programmatic stream serialisation
 inline unsigned fill_launch_attrs(cudaLaunchAttribute *attr, unsigned cluster)

@@ -317,6 +317,7 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
     per = ((per + kThreads - 1) / kThreads) * kThreads;
     if (per < kThreads) per = kThreads;
     if (per > 8 * kThreads) per = 8 * kThreads;
+    if (fwd_px_per_cta_override() > 0) per = fwd_px_per_cta_override();
     p.px_per_cta = (int)per;
     p.ctas_per_crop = (int)((npx + per - 1) / per);
     const long long ctas = (long long)p.N * p.ctas_per_crop;
