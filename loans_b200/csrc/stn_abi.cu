@@ -39,6 +39,7 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement);   // -1: use the general kernel
 void band_tuning(int which, int value);
+int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not taken
 int launch_prepare_images(const float *x, float *out, float scale, int b, int h, int w, cudaStream_t stream);      // -1: shape not supported, use the general kernel
 
 static std::atomic<int> g_force_general{0};
@@ -100,6 +101,11 @@ static int crop_bwd_dispatch(const CropParams &p, float mask01, int k, int c, in
     // for narrow frames and enough crops, CTA bands for wide frame rows; the rule is in launch_crop_bwd_band);
     // LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on (wherever it applies) / off.
     const int band = g_band_backward.load();
+    // frames without grad, rotation masked: the table-driven theta kernel (any number of crops per frame)
+    if (mask01 == 0.0f && gx == nullptr && band != 0 && theta_only_kernel_enabled() && !g_force_general.load()) {
+        const int rc = launch_crop_bwd_theta_tab(p, gy_dtype, stream);
+        if (rc >= 0) return rc;
+    }
     if (mask01 == 0.0f && k == 1 && gx != nullptr && band != 0 && !g_force_general.load()) {
         const int rc = launch_crop_bwd_band(p, gy_dtype, stream, band < 0);
         if (rc >= 0) return rc;

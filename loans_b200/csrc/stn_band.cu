@@ -507,6 +507,133 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
 #endif                                                 // shared memory stays valid until the TMA unit has read it
 }
 
+// ------------------------------------------------------------------------------------------ frames without grad
+// gx == NULL (every LoANs call: the frames are a raw array) and rotation terms masked: the theta gradient alone, with the
+// coordinate chains taken from per-crop BandAxis tables (oW + rows entries per CTA) instead of being re-derived per pixel --
+// the per-pixel work is two 16-byte table reads, 4 taps x C + gy, and the exact d/du, d/dv arithmetic.  Any number of crops
+// per frame, any sign of the scales (nothing is scattered, so nothing can collide).  Crops whose rotation terms are not
+// (+-)0 after masking run the general theta role in the same launch.
+template <typename GT, int CG, bool GRAY>
+__global__ void __launch_bounds__(kThreads, 4) stn_bwd_theta_tab_kernel(const __grid_constant__ CropParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
+    BandAxis *coltab = reinterpret_cast<BandAxis *>(smem_raw + sizeof(BwdSmem));
+    BandAxis *rowtab = coltab + p.oW;
+    float *xs = reinterpret_cast<float *>(rowtab + p.band_rows_cta);
+    float *ys = xs + p.oW;
+    const int cs = p.ctas_per_crop;
+    const int n = blockIdx.x / cs, rank = blockIdx.x - n * cs;
+    const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    push_reduce_init(sm, rank, cs);
+    pdl_wait();
+    const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
+    const float mag = fabsf(th.t00) + fabsf(th.t11) + fabsf(th.t02) + fabsf(th.t12);
+    if (!(th.t01 == 0.0f && th.t10 == 0.0f && mag < 1e30f)) {           // rotated (or non-finite) crop: per-pixel chains
+        fill_axis_tables(p, xs, ys);
+        __syncthreads();
+        theta_role<GT, CG, true, GRAY>(p, xs, ys, sm, (int)blockIdx.x);
+        return;
+    }
+    const int H = p.H, W = p.W, oH = p.oH, oW = p.oW;
+    const int i0 = rank * p.band_rows_cta, i1 = min(oH, i0 + p.band_rows_cta);
+    for (int k = tid; k < oW + max(i1 - i0, 0); k += kThreads) {
+        if (k < oW) coltab[k] = make_band_axis(th.t00, th.t01, th.t02, lin_x_at(p, k), true, W);
+        else rowtab[k - oW] = make_band_axis(th.t11, th.t10, th.t12, lin_y_at(p, i0 + k - oW), false, H);
+    }
+    __syncthreads();
+    const int npx = oH * oW, plane = H * W;
+    const float *xb = p.x + (size_t)(n / p.K) * CG * plane;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : CG) * npx;
+    float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
+    const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int q_end = i1 * oW;
+    for (PxWalk w(i0 * oW + tid, oW); w.q < q_end; w.next()) {
+        const BandAxis col = coltab[w.j], row = rowtab[w.i - i0];
+        const Tap t = tap_from_band_axes(col, row, H, W);
+        const TapAddr a = make_tap_addr(t, H, W);
+        float v[CG][4], g[CG];
+        const GT *gp = gyb + w.q;
+#pragma unroll
+        for (int ch = 0; ch < CG; ++ch) {
+            load_taps(xb + ch * plane, a, W, v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+            g[ch] = load_gy<GT, GRAY>(gp, ch, npx);
+        }
+        float su = 0.f, sv = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < CG; ++ch) {
+            float gu, gv;
+            grad_uv(t, v[ch][0], v[ch][1], v[ch][2], v[ch][3], gu, gv);
+            gu = f_mul(gu, g[ch]);
+            gv = f_mul(gv, g[ch]);
+            if (ch == 0) { su = gu; sv = gv; }
+            else { su = f_add(su, gu); sv = f_add(sv, gv); }                  // numpy.sum over the channel axis
+        }
+        finish_grad_uv(t, H, W, su, sv);
+        if (ggo) {
+            ggo[w.q] = su;
+            ggo[npx + w.q] = sv;
+        }
+        if (ggu) {
+            su = f_add(su, __ldg(ggu + w.q));
+            sv = f_add(sv, __ldg(ggu + npx + w.q));
+        }
+        s[0] = fmaf(su, col.lin, s[0]); s[1] = fmaf(su, row.lin, s[1]); s[2] += su;
+        s[3] = fmaf(sv, col.lin, s[3]); s[4] = fmaf(sv, row.lin, s[4]); s[5] += sv;
+    }
+    reduce_gtheta_push(p, s, sm, n, rank, cs);
+}
+
+template <typename GT, int CG, bool GRAY>
+static cudaError_t launch_theta_tab_tt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, cs);
+    return cudaLaunchKernelEx(&cfg, stn_bwd_theta_tab_kernel<GT, CG, GRAY>, p);
+}
+
+// Returns -1 when the call is not one this kernel takes (gx wanted, rotation not masked, channel count not 1 / 3 / 4).
+int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream)
+{
+    if (p.gx || p.mask01 != 0.0f) return -1;
+    if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
+    if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
+    if ((long long)p.H * p.W * p.C > 0x7fffffffLL) return -1;
+    // CTAs per crop: enough to fill the machine (as the general theta role), at most 8, at least 64 pixels per thread-block row
+    const long long npx = (long long)p.oH * p.oW;
+    unsigned cs = 1;
+    while (cs < 8 && (long long)p.N * cs < 2LL * kNumSMs && (int)(2 * cs) <= p.oH && npx / (2 * cs) >= kThreads / 2) cs *= 2;
+    p.ctas_per_crop = (int)cs;
+    p.px_per_cta = (int)((npx + cs - 1) / cs);                         // rotated crops: the general theta role's share
+    p.band_rows_cta = (p.oH + (int)cs - 1) / (int)cs;
+    const size_t smem = sizeof(BwdSmem) + sizeof(BandAxis) * (size_t)(p.oW + p.band_rows_cta) + sizeof(float) * (size_t)((p.oW + p.oH + 3) & ~3);
+    if (smem > 48 * 1024) return -1;
+    const long long ctas = (long long)p.N * cs;
+    if (ctas > 0x7fffffffLL) return -1;
+    cudaError_t e;
+    if (gy_dtype == 0)
+        e = p.C == 1 ? launch_theta_tab_tt<float, 1, false>(p, (unsigned)ctas, cs, smem, stream)
+          : p.C == 4 ? launch_theta_tab_tt<float, 4, false>(p, (unsigned)ctas, cs, smem, stream)
+          : p.gray   ? launch_theta_tab_tt<float, 3, true>(p, (unsigned)ctas, cs, smem, stream)
+                     : launch_theta_tab_tt<float, 3, false>(p, (unsigned)ctas, cs, smem, stream);
+    else
+        e = p.C == 1 ? launch_theta_tab_tt<__nv_bfloat16, 1, false>(p, (unsigned)ctas, cs, smem, stream)
+          : p.C == 4 ? launch_theta_tab_tt<__nv_bfloat16, 4, false>(p, (unsigned)ctas, cs, smem, stream)
+          : p.gray   ? launch_theta_tab_tt<__nv_bfloat16, 3, true>(p, (unsigned)ctas, cs, smem, stream)
+                     : launch_theta_tab_tt<__nv_bfloat16, 3, false>(p, (unsigned)ctas, cs, smem, stream);
+    count_launch();
+    if (e != cudaSuccess) return set_error("crop_bwd (theta, tables) launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ host launcher
 // tuning knobs (loans_stn_configure): 0 = automatic
 static int g_band_cs = 0, g_band_rows = 0, g_band_tile_kb = 0, g_band_variant = 0;

@@ -318,3 +318,43 @@ def test_band_backward_full_size_adjoint(G):
     assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-3, (lhs, rhs)
     gt0, gx0, _ = oc.crop_backward(d["x"][:4], d["theta"][:4], osz, d["gy"][:4], None, 0.0, 1)
     assert G.rel_max(gx[:4], gx0) <= 2e-6 and G.rel_max(gt[:4], gt0) <= GRAD_TOL
+
+
+# ------------------------------------------------------------------------------------------------ frames without grad
+@pytest.mark.parametrize("name,batch,bf16", [("cfg1", None, False), ("cfg2", 16, False), ("cfg3", 6, True), ("cfg4", 3, False), ("cfg5", 24, False)])
+def test_theta_gradient_without_gx_table_kernel(G, name, batch, bf16):
+    """gx == NULL with the rotation terms masked (every LoANs call): the table-driven theta kernel -- any number of crops per
+    frame, mirrored and up-sampling boxes included -- against the oracle; the per-pixel grid gradient stays bit-exact."""
+    from loans_b200 import _lib
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=True, with_ggrid=True)
+    d["theta"][::5, :, 2] += 0.9                      # hanging out of the frame
+    d["theta"][1::7, 0, 0] *= -1.0                    # mirrored
+    d["theta"][2::9, :, :2] *= 0.2                    # up-sampling
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    gy = G.bf16_round(d["gy"]) if bf16 else d["gy"]
+    n0 = _lib.launch_count()
+    gt, gx, ggo = G.crop_bwd(d["x"], d["theta"], osz, gy, d["ggrid"], 0.0, k, bf16=bf16, need_gx=False)
+    assert _lib.launch_count() - n0 == 1 and gx is None
+    gt0, _, gg0 = oc.crop_backward(d["x"], d["theta"], osz, gy, d["ggrid"], 0.0, k)
+    assert np.array_equal(ggo, gg0)
+    assert np.abs(gt - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max())
+    try:                                              # and the same through the general theta-only kernel
+        _lib.band_backward(False)
+        gt1, _, ggo1 = G.crop_bwd(d["x"], d["theta"], osz, gy, d["ggrid"], 0.0, k, bf16=bf16, need_gx=False)
+    finally:
+        _lib.band_backward(None)
+    assert np.array_equal(ggo1, gg0) and G.rel_max(gt1, gt) <= 1e-5
+
+
+def test_theta_gradient_without_gx_hard_boxes(G):
+    rng = np.random.default_rng(4)
+    for shape in ((3, 24, 24, 9, 9), (1, 8, 8, 16, 16), (3, 20, 12, 1, 5), (4, 13, 9, 6, 1), (3, 33, 45, 20, 30)):
+        c, h, w, oh, ow = shape
+        x = rng.random((len(BAND_THETAS), c, h, w), dtype=np.float32)
+        gy = rng.standard_normal((len(BAND_THETAS), c, oh, ow)).astype(np.float32)
+        gt, _, ggo = G.crop_bwd(x, BAND_THETAS, (oh, ow), gy, None, 0.0, 1, need_gx=False)
+        gt0, _, gg0 = oc.crop_backward(x, BAND_THETAS, (oh, ow), gy, None, 0.0, 1)
+        assert np.array_equal(ggo, gg0)
+        assert np.abs(gt - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max())
