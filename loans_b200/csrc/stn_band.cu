@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
 #ifndef STN_BAND_PULL_REDUCE
     push_reduce_init(sm, rank, cs);                                   // shared memory only: before the wait
 #endif
+    pdl_prefetch_theta(p, n);
+#ifdef STN_NO_PDL_PREFETCH
     pdl_wait();
-    {   // this CTA's gy rows do not depend on theta: start them towards L2 while theta is on its way
+#endif
+    {   // this CTA's gy rows do not depend on theta: started towards L2 before the wait (prefetches only, see pdl_prefetch_theta)
         const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
         const int row_elems = max(r1 - r0, 0) * p.oW;
         const int lines = (row_elems * (int)sizeof(GT) + 127) / 128;
@@ -123,6 +126,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
     }
+#ifndef STN_NO_PDL_PREFETCH
+    pdl_wait();
+#endif
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     TRACE(1);
     const int H = p.H, W = p.W, oH = p.oH, oW = p.oW;
@@ -527,6 +533,7 @@ __global__ void __launch_bounds__(kThreads, 4) stn_bwd_theta_tab_kernel(const __
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     push_reduce_init(sm, rank, cs);
+    pdl_prefetch_theta(p, n);
     pdl_wait();
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const float mag = fabsf(th.t00) + fabsf(th.t11) + fabsf(th.t02) + fabsf(th.t12);

@@ -117,6 +117,21 @@ __device__ __forceinline__ void fill_axis_tables(const CropParams &p, float *xs,
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// L2 prefetches are the one kind of global access that may come BEFORE pdl_wait(): nothing is read into registers and L2 is
+// the point of coherence, so whatever the previous kernel still writes is what a later load sees.  The first warp of a CTA
+// asks for the 128-byte lines of theta from its own crop onwards (32 lines = 170 crops): the CTAs that become resident
+// while the previous kernel drains warm theta for the ones behind them.
+__device__ __forceinline__ void pdl_prefetch_theta(const CropParams &p, int n)
+{
+#ifndef STN_NO_PDL_PREFETCH
+    if (threadIdx.x < 32) {
+        const char *base = reinterpret_cast<const char *>(p.theta);
+        const size_t bytes = 24 * (size_t)p.N, off = 24 * (size_t)n + 128 * (size_t)threadIdx.x;
+        if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+#endif
+}
+
 // ---- host-side error plumbing (definitions in stn_abi.cu)
 int set_error(const char *fmt, ...);
 void count_launch(int n = 1);

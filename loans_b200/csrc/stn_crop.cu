@@ -47,12 +47,13 @@ __global__ void __launch_bounds__(kThreads, FwdMinCtas<YT>::value) stn_fwd_kerne
     extern __shared__ float smem[];
     float *xs = smem, *ys = smem + p.oW;
     pdl_launch_dependents();
+    const int n = blockIdx.x / p.ctas_per_crop;
     if (!FROM_GRID) {
+        pdl_prefetch_theta(p, n);
         fill_axis_tables(p, xs, ys);                 // pure arithmetic: overlaps the tail of the previous kernel
         __syncthreads();
     }
     pdl_wait();
-    const int n = blockIdx.x / p.ctas_per_crop;
     const int tile = blockIdx.x - n * p.ctas_per_crop;
     const int npx = p.oH * p.oW;
     const int q_end = min(npx, (tile + 1) * p.px_per_cta);
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 4) stn_bwd_theta_kernel(const __grid
     float *xs = reinterpret_cast<float *>(smem_raw + sizeof(BwdSmem));
     float *ys = xs + p.oW;
     pdl_launch_dependents();
+    pdl_prefetch_theta(p, (int)blockIdx.x / p.ctas_per_crop);
     fill_axis_tables(p, xs, ys);
     pdl_wait();
     __syncthreads();
