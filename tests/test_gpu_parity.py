@@ -358,3 +358,40 @@ def test_theta_gradient_without_gx_hard_boxes(G):
         gt0, _, gg0 = oc.crop_backward(x, BAND_THETAS, (oh, ow), gy, None, 0.0, 1)
         assert np.array_equal(ggo, gg0)
         assert np.abs(gt - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max())
+
+
+@pytest.mark.parametrize("name,batch,mask", [("cfg1", None, 0.0), ("cfg2", 8, 1.0)])
+def test_reference_gpu_kernels_agree_with_oracle_and_cuda_path(G, name, batch, mask):
+    """A second witness for the conventions the oracle restates (align-corners pixel map, zero padding, grid channel
+    order, gradient scaling): cuDNN's cudnnSpatialTfGridGenerator / cudnnSpatialTfSampler, forward and backward -- the
+    kernels chainer 4.1.0 itself runs for F.spatial_transformer_grid / _sampler on a GPU --
+    driven through baseline/cudnn_stn.py on the same inputs.  cuDNN's arithmetic is not the numpy path's (fused
+    multiply-adds, atomics for gx), so the bar is north_star's gradient tolerance, not bit-exactness."""
+    import torch
+    from baseline.cudnn_stn import CudnnStn
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, seed=5, batch=batch)
+    x, theta, gy = d["x"], d["theta"], d["gy"]
+    b, c, h, w = x.shape
+    osz = (wl.out_h, wl.out_w)
+    try:
+        stn = CudnnStn(b, c, h, w, osz[0], osz[1], G.DEV)
+    except RuntimeError as e:                              # no libcudnn on this box: nothing to compare with
+        pytest.skip(str(e))
+    stn.set_stream(torch.cuda.current_stream().cuda_stream)
+    xd, td, gyd = G.dev(x), G.dev(theta), G.dev(gy)
+    f32 = dict(dtype=torch.float32, device=G.DEV)
+    y_c, grid2 = torch.empty((b, c) + osz, **f32), torch.empty((b,) + osz + (2,), **f32)
+    grid_c, dgrid2 = torch.empty((b, 2) + osz, **f32), torch.empty((b,) + osz + (2,), **f32)
+    gx_c, gt_c = torch.empty((b, c, h, w), **f32), torch.empty((b, 2, 3), **f32)
+    stn.forward(xd, td, mask, y_c, grid2, grid_c)
+    stn.backward(xd, None, mask, gyd, grid2, gx_c, dgrid2, gt_c)
+    torch.cuda.synchronize()
+    y, grid = G.crop_fwd(x, theta, osz, mask, 1)
+    gt, gx, _ = G.crop_bwd(x, theta, osz, gy, None, mask, 1)
+    y0, grid0 = oc.crop_forward(x, theta, osz, mask, 1)
+    gt0, gx0, _ = oc.crop_backward(x, theta, osz, gy, None, mask, 1)
+    for what, ours, orc, ref in (("grid", grid, grid0, grid_c), ("y", y, y0, y_c), ("gx", gx, gx0, gx_c), ("gtheta", gt, gt0, gt_c)):
+        ref = ref.cpu().numpy()
+        assert G.rel_max(orc, ref) <= GRAD_TOL, (what, "oracle vs cuDNN", G.rel_max(orc, ref))
+        assert G.rel_max(ours, ref) <= GRAD_TOL, (what, "CUDA path vs cuDNN", G.rel_max(ours, ref))
