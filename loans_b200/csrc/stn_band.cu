@@ -746,6 +746,19 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool b
             if (!rowband && slot_bytes < 4096) return -1;
         }
     }
+    if (rowband && g_band_cs == 0) {
+        // among the cluster sizes that keep the warps equally busy, the smallest one (>= 2) that still launches ~1.7 waves of
+        // CTAs (4 x 148 resident): fewer CTAs per crop amortise the per-CTA prologue and reduction.  Measured, 75x75 crops:
+        // 125.5 vs 127.3 us at 512 crops and 228.0 vs 238.7 us at 1024 (2 vs 5 CTAs per crop; a tie at 256); 64x64 crops:
+        // 49.1 vs 53.0 us at 256 (4 vs 8), 91.9 vs 99.6 us at 512 (2 vs 8); one CTA per crop loses everywhere (267 us at 1024)
+        const int rows_big = (p.oH + (int)cs_row - 1) / (int)cs_row;
+        const double util_big = (double)p.oH / ((double)cs_row * kWarps * ((rows_big + kWarps - 1) / kWarps));
+        for (unsigned c = 2; c < cs_row; ++c) {
+            const int rows = (p.oH + (int)c - 1) / (int)c;
+            const double util = (double)p.oH / ((double)c * kWarps * ((rows + kWarps - 1) / kWarps));
+            if (util >= util_big * 0.999 && (long long)p.N * c >= 1024) { cs_row = c; break; }
+        }
+    }
     if (rowband) cs = cs_row;
     p.ctas_per_crop = (int)cs;
     p.px_per_cta = (int)(((long long)p.oH * p.oW + cs - 1) / cs);     // declined crops: theta role share
