@@ -302,6 +302,33 @@ def test_band_backward_matches_the_general_kernel(G, name, batch):
     assert G.rel_max(b1[1], gx0) <= 2e-6 and G.rel_max(b1[0], gt0) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("cs", [1, 2, 3, 5])
+def test_row_bands_with_few_ctas_per_crop(G, cs):
+    """Row bands with 1 / 2 / 3 / 5 CTAs per crop: every warp then works through several crop rows, one after the other,
+    on its private tile (at full size the launcher takes 2 CTAs per crop from 512 crops of 75 rows).  Same results,
+    bit for bit, as with the automatic choice, and the oracle's within the usual bars."""
+    from loans_b200 import _lib
+    wl = W.WORKLOADS["cfg5"]
+    d = W.make_inputs(wl, batch=12, rotate=True, with_ggrid=True, seed=31)
+    d["theta"][::5, :, 2] += 0.9
+    d["theta"][2::4, :, :2] *= 0.3                    # up-sampling crops: phased scatter, halo rows
+    osz = (wl.out_h, wl.out_w)
+    try:
+        _lib.band_backward(True)
+        _lib.band_tuning(variant=3)
+        b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+        _lib.band_tuning(variant=3, cs=cs)
+        b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+    finally:
+        _lib.band_tuning()
+        _lib.band_backward(None)
+    assert np.array_equal(b1[1], b0[1]) and np.array_equal(b1[2], b0[2])          # gx, ggrid: bit-identical
+    assert G.rel_max(b1[0], b0[0]) <= 1e-5                                        # gtheta: the partial sums group differently
+    gt0, gx0, gg0 = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, 1)
+    assert np.array_equal(b1[2], gg0)
+    assert G.rel_max(b1[1], gx0) <= 2e-6 and G.rel_max(b1[0], gt0) <= GRAD_TOL
+
+
 def test_band_backward_full_size_adjoint(G):
     from loans_b200 import _lib
     wl = W.WORKLOADS["cfg2"]
