@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LOANS_STN_ABI_VERSION 1
+#define LOANS_STN_ABI_VERSION 2
 
 /* element type of the crops y / gy */
 #define LOANS_STN_F32  0
@@ -47,36 +47,25 @@ int loans_stn_abi_version(void);
 const char *loans_stn_last_error(void);
 /* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
 unsigned long long loans_stn_launch_count(void);
+/* names of the kernels the LAST compute entry point called in this process launched, '+'-separated (e.g.
+ * "stn_bwd_band_kernel/row"; process-wide, since a backward usually runs on the framework's autograd thread): lets tests
+ * and bench.py state which kernel a dispatch rule picked */
+const char *loans_stn_last_kernel(void);
 
-/* process-wide switches, for tests and A/B measurements (results are bit-identical either way).
- * LOANS_STN_CFG_TMA_FORWARD != 0: forward of axis-aligned crops (mask01 == 0, w % 4 == 0) through the AxisTap-table +
- *   TMA-bulk-copy-staged kernel (stn_separable.cu) instead of the direct gather.  Default 0: on B200 the direct gather
- *   measured faster at every BASELINE size (profiles/README.md).
- * LOANS_STN_CFG_FORCE_GENERAL != 0: never take an axis-aligned kernel, whatever the other switches say.
- * LOANS_STN_CFG_BAND_BACKWARD: backward of axis-aligned crops (mask01 == 0, one crop per frame, gx wanted, w % 4 == 0)
- *   through the band kernels (stn_band.cu).  -1 (default): where they measured faster (row bands: narrow frames and enough
- *   crops to fill the machine, e.g. 64 crops of 64 rows from 224-px frames; CTA bands: frame rows of >= 4 KiB, e.g. 512-px
+/* process-wide switches (results are identical either way; further test hooks in loans_stn_devel.h).
+ * LOANS_STN_CFG_FORCE_GENERAL != 0: never take a kernel written for axis-aligned crops.
+ * LOANS_STN_CFG_BAND_BACKWARD: backward of axis-aligned crops (one crop per frame, gx wanted, w % 4 == 0) through the
+ *   band kernels (stn_band.cu).  -1 (default): where they measured faster (row bands: narrow frames and enough crops to
+ *   fill the machine, e.g. 64 crops of 64 rows from 224-px frames; CTA bands: frame rows of >= 4 KiB, e.g. 512-px
  *   frames), 1: whenever they apply, 0: never.  gx, ggrid: same values; gtheta: same sums in a different order (both
  *   within the 1e-4 bar).
- * LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: tuning knobs of the band kernel for A/B measurements
- *   (CTAs per crop, crop rows per band, shared-memory tile budget in KiB, kernel variant: 1, 2 CTA bands, 3 row bands);
- *   0 = automatic.
- * LOANS_STN_CFG_PDL (default 1): the fused kernels (crop_fwd, crop_bwd, sampler_fwd) are launched with programmatic
- *   stream serialisation: their CTAs may become resident, and fill their shared-memory tables, while the previous kernel of
- *   the stream is still draining; they touch global memory only after griddepcontrol.wait, so stream order is preserved
- *   whatever the neighbouring kernels are.  0: plain launches. */
+ * LOANS_STN_CFG_PDL (default 1): the fused kernels are launched with programmatic stream serialisation: their CTAs may
+ *   become resident, and fill their shared-memory tables, while the previous kernel of the stream is still draining; they
+ *   touch global memory only after griddepcontrol.wait, so stream order is preserved whatever the neighbouring kernels
+ *   are.  0: plain launches. */
 #define LOANS_STN_CFG_FORCE_GENERAL 1
-#define LOANS_STN_CFG_TMA_FORWARD 2
 #define LOANS_STN_CFG_BAND_BACKWARD 3
-#define LOANS_STN_CFG_BAND_CS 4
-#define LOANS_STN_CFG_BAND_ROWS 5
-#define LOANS_STN_CFG_BAND_TILE_KB 6
-#define LOANS_STN_CFG_BAND_VARIANT 7
 #define LOANS_STN_CFG_PDL 8
-#define LOANS_STN_CFG_GX_TILES_PER_WARP 10   /* general backward: frame tiles per warp of the gx role, 0 = automatic (A/B) */
-#define LOANS_STN_CFG_THETA_ONLY_KERNEL 11 /* gx == NULL: the theta-only kernel (default 1); 0: the two-role kernel without gx CTAs (A/B) */
-#define LOANS_STN_CFG_FWD_PX_PER_CTA 12    /* forward: crop pixels per CTA (rounded up to 256); 0 = automatic (A/B) */
-#define LOANS_STN_CFG_THETA_FIRST 9   /* general backward: schedule the theta-role CTAs before the gx-role CTAs (A/B) */
 int loans_stn_configure(int key, int value);
 
 /* ---- a1  rotation_dropout forward AND backward: out = in * mask, mask = 1 except [.,0,1] = [.,1,0] = mask01.
@@ -147,6 +136,18 @@ int loans_stn_crop_bwd_corners(const float *x, const float *theta, float mask01,
  *      coef[ch] * gy to channel ch, so the 3-channel crops are never written or read.  grid, corners (fwd) and
  *      ggrid_upstream, gcorners, gx, ggrid_out (bwd) may each be NULL.  With flags == 0 these are the entry points above. */
 #define LOANS_STN_FLAG_GRAY 1
+/* LOANS_STN_FLAG_UPRIGHT (bwd): the caller asserts that theta's rotation terms are already zero although mask01 != 0 --
+ *      theta is the OUTPUT of a rotation dropout that zeroed them (the strict three-node use of the reference operators:
+ *      rotation_dropout -> grid -> sampler with the masked theta materialised in between).  It selects the same kernels
+ *      as mask01 == 0.  A hint only: those kernels test every crop's own rotation terms on the device and run the general
+ *      roles for a crop that is rotated after all, in the same launch -- a wrong hint costs time, never correctness. */
+#define LOANS_STN_FLAG_UPRIGHT 2
+/* LOANS_STN_FLAG_NHWC4 (c == 3, bf16 crops, no GRAY): y / gy are channels-last with the channel count padded to four,
+ *      (n, oh, ow, 4) bf16 -- one 8-byte store / load per crop pixel, the layout a tensor-core first convolution of the
+ *      assessor consumes (reference common/net.py:15-25,77-90 is the consumer; Chainer itself only has float32 NCHW).
+ *      fwd writes the padding channel as +0; bwd ignores it.  Values are those of the bf16 NCHW crops. */
+#define LOANS_STN_FLAG_NHWC4 4
+#define LOANS_STN_FLAGS_ALL 7
 int loans_stn_crop_fwd_ex(const float *x, const float *theta, float mask01, void *y, float *grid, float *corners,
                           int flags, int n, int k, int c, int h, int w, int oh, int ow, int y_dtype, void *stream);
 int loans_stn_crop_bwd_ex(const float *x, const float *theta, float mask01, const void *gy, const float *ggrid_upstream,

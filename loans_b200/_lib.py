@@ -8,15 +8,17 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libloans_stn.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, BF16 = 0, 1
-FLAG_GRAY = 1
+FLAG_GRAY, FLAG_UPRIGHT, FLAG_NHWC4 = 1, 2, 4
 CFG_FORCE_GENERAL = 1
-CFG_TMA_FORWARD = 2
 CFG_BAND_BACKWARD = 3
 CFG_PDL = 8
-CFG_THETA_FIRST = 9
+# include/loans_stn_devel.h: test hooks (always there) ...
 CFG_BAND_CS, CFG_BAND_ROWS, CFG_BAND_TILE_KB, CFG_BAND_VARIANT = 4, 5, 6, 7
+# ... and A/B switches of a -DSTN_DEVEL build (the product build answers them with an error)
+CFG_TMA_FORWARD = 2
+CFG_THETA_FIRST = 9
 
 _lib = None
 
@@ -29,6 +31,7 @@ SIGNATURES = {
     "loans_stn_abi_version": [],
     "loans_stn_last_error": [],
     "loans_stn_launch_count": [],
+    "loans_stn_last_kernel": [],
     "loans_stn_configure": [_i, _i],
     "loans_stn_rotation_dropout": [_vp, _fl, _vp, _i, _vp],
     "loans_stn_prepare_images": [_vp, _fl, _vp, _i, _i, _i, _i, _vp],
@@ -45,6 +48,12 @@ SIGNATURES = {
 }
 
 
+# include/loans_stn_devel.h
+DEVEL_SIGNATURES = {
+    "loans_stn_probe": [_i, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _vp],
+}
+
+
 class StnLibraryError(RuntimeError):
     pass
 
@@ -57,12 +66,13 @@ def lib():
                 "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). loans_b200 has no CPU or PyTorch fallback." % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
-        for name, argtypes in SIGNATURES.items():
+        for name, argtypes in list(SIGNATURES.items()) + list(DEVEL_SIGNATURES.items()):
             fn = getattr(handle, name)           # AttributeError if the ABI lost a symbol
             fn.argtypes = argtypes
             fn.restype = _i
         handle.loans_stn_last_error.restype = ctypes.c_char_p
         handle.loans_stn_launch_count.restype = ctypes.c_ulonglong
+        handle.loans_stn_last_kernel.restype = ctypes.c_char_p
         if handle.loans_stn_abi_version() != ABI_VERSION:
             raise StnLibraryError("libloans_stn.so ABI %d != expected %d" % (handle.loans_stn_abi_version(), ABI_VERSION))
         _lib = handle
@@ -80,7 +90,7 @@ def force_general(on):
 
 
 def tma_forward(on):
-    """Opt into the TMA-staged forward kernel for axis-aligned crops (mask01 == 0)."""
+    """-DSTN_DEVEL builds only: the TMA-staged forward kernel for axis-aligned crops (mask01 == 0)."""
     check(lib().loans_stn_configure(CFG_TMA_FORWARD, int(bool(on))), "loans_stn_configure")
 
 
@@ -107,3 +117,8 @@ def band_tuning(cs=0, rows=0, tile_kb=0, variant=0):
 
 def launch_count():
     return int(lib().loans_stn_launch_count())
+
+
+def last_kernel():
+    """'+'-separated names of the kernels this thread's last compute call launched (which one a dispatch rule picked)."""
+    return lib().loans_stn_last_kernel().decode()

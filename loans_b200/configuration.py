@@ -10,6 +10,9 @@ import threading
 
 class _Config(threading.local):
     train = True
+    # rotation_dropout / spatial_transformer_grid return deferred tensors so that the reference's three calls run as one
+    # fused kernel per direction (loans_b200/functions/spatial_transformer.py); False: three eager operator nodes
+    defer = True
 
 
 config = _Config()

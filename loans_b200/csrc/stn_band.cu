@@ -610,14 +610,14 @@ static cudaError_t launch_theta_tab_tt(const CropParams &p, unsigned ctas, unsig
 // Returns -1 when the call is not one this kernel takes (gx wanted, rotation not masked, channel count not 1 / 3 / 4).
 int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream)
 {
-    if (p.gx || p.mask01 != 0.0f) return -1;
+    if (p.gx) return -1;
     if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
     if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
     if ((long long)p.H * p.W * p.C > 0x7fffffffLL) return -1;
     // CTAs per crop: enough to fill the machine (as the general theta role), at most 8, at least 64 pixels per thread-block row
     const long long npx = (long long)p.oH * p.oW;
     unsigned cs = 1;
-    while (cs < 8 && (long long)p.N * cs < 2LL * kNumSMs && (int)(2 * cs) <= p.oH && npx / (2 * cs) >= kThreads / 2) cs *= 2;
+    while (cs < 8 && (long long)p.N * cs < 2LL * num_sms() && (int)(2 * cs) <= p.oH && npx / (2 * cs) >= kThreads / 2) cs *= 2;
     p.ctas_per_crop = (int)cs;
     p.px_per_cta = (int)((npx + cs - 1) / cs);                         // rotated crops: the general theta role's share
     p.band_rows_cta = (p.oH + (int)cs - 1) / (int)cs;
@@ -637,6 +637,7 @@ int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream)
           : p.gray   ? launch_theta_tab_tt<__nv_bfloat16, 3, true>(p, (unsigned)ctas, cs, smem, stream)
                      : launch_theta_tab_tt<__nv_bfloat16, 3, false>(p, (unsigned)ctas, cs, smem, stream);
     count_launch();
+    note_kernel("stn_bwd_theta_tab_kernel");
     if (e != cudaSuccess) return set_error("crop_bwd (theta, tables) launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -655,13 +656,9 @@ void band_tuning(int which, int value)
 template <typename GT, int CG, int ILP, int MINB, bool GRAY = false, bool ROWBAND = false>
 static cudaError_t launch_band_ttt(const CropParams &p, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
-    if (smem > 48 * 1024) {
-        static size_t granted = 0;
-        if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY, ROWBAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            granted = smem;
-        }
+    {
+        const cudaError_t e = grant_dynamic_smem(reinterpret_cast<const void *>(&stn_bwd_band_kernel<GT, CG, ILP, MINB, GRAY, ROWBAND>), smem);
+        if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -686,7 +683,9 @@ static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned c
     }
     switch (kind) {
     case 3: return launch_band_ttt<GT, CG, 1, 4, false, true>(p, ctas, cs, smem, s);
+#ifdef STN_DEVEL
     case 2: return launch_band_ttt<GT, CG, 2, 3>(p, ctas, cs, smem, s);
+#endif
     default: return launch_band_ttt<GT, CG, 1, 4>(p, ctas, cs, smem, s);
     }
 }
@@ -700,7 +699,7 @@ static cudaError_t launch_band_tt(const CropParams &p, unsigned ctas, unsigned c
 //   CTA bands: frame rows of at least 4 KiB (512-px RGB frames: 192 vs 209-214 us at BASELINE config 3).
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement)
 {
-    if (!p.gx || p.K != 1 || p.mask01 != 0.0f) return -1;
+    if (!p.gx || p.K != 1) return -1;
     if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
     if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.gx) & 15) != 0) return -1;
     if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
@@ -812,6 +811,7 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool b
           : p.C == 3 ? launch_band_tt<__nv_bfloat16, 3>(p, (unsigned)ctas, cs, smem, stream, kind)
                      : launch_band_tt<__nv_bfloat16, 4>(p, (unsigned)ctas, cs, smem, stream, kind);
     count_launch();
+    note_kernel(rowband ? "stn_bwd_band_kernel/row" : "stn_bwd_band_kernel/cta");
     if (e != cudaSuccess) return set_error("crop_bwd (band) launch failed: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -10,7 +10,15 @@ namespace stn {
 
 constexpr int kThreads = 256;       // threads per CTA, every kernel
 constexpr int kWarps = kThreads / 32;
-constexpr int kNumSMs = 148;        // B200
+
+// multiprocessors of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on B200): the grid-size
+// rules are written in multiples of it
+int num_sms();
+// opt a kernel into more than 48 KiB of dynamic shared memory on the CURRENT device (the attribute is per device and per
+// function: cached per (function, device), safe from several threads)
+cudaError_t grant_dynamic_smem(const void *func, size_t bytes);
+// name of the kernel a launcher picked, for loans_stn_last_kernel() (thread-local, last compute call)
+void note_kernel(const char *name);
 
 // One parameter block for the whole family; unused pointers are null.
 struct CropParams {
@@ -27,6 +35,7 @@ struct CropParams {
     float *ggrid_out;        // (N,2,oH,oW) or null
     float *corners_out;      // (N,2,2,2) or null: the grid at its four corners [., ., {0,oH-1}, {0,oW-1}] (forward)
     const float *gcorners;   // (N,2,2,2) or null: gradient arriving on those four grid points (backward)
+    int nhwc;                // C == 3, bf16 only: y / gy are (N,oH,oW,4) channels-last, channel count padded to four
     int gray;                // C == 3 only: y / gy are (N,1,oH,oW), y = 0.299*ch2 + 0.587*ch1 + 0.114*ch0 (see gray_coef)
     int N, K, C, H, W, oH, oW;
     double xstep, ystep;     // 2/(oW-1), 2/(oH-1)

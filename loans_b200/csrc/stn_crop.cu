@@ -320,7 +320,7 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
     if (p.N == 0) return 0;
     const long long npx = (long long)p.oH * p.oW;
     // enough CTAs to give every SM a few, at most 8 pixels per thread
-    long long per = (npx * p.N + 4LL * kNumSMs - 1) / (4LL * kNumSMs);
+    long long per = (npx * p.N + 4LL * num_sms() - 1) / (4LL * num_sms());
     per = ((per + kThreads - 1) / kThreads) * kThreads;
     if (per < kThreads) per = kThreads;
     if (per > 8 * kThreads) per = 8 * kThreads;
@@ -340,6 +340,7 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
         e = from_grid ? launch_fwd_t<__nv_bfloat16, true>(p, cgsel, grid, smem, stream)
                       : launch_fwd_t<__nv_bfloat16, false>(p, cgsel, grid, smem, stream);
     count_launch();
+    note_kernel(from_grid ? "stn_fwd_kernel/grid" : "stn_fwd_kernel");
     if (e != cudaSuccess) return set_error("crop_fwd launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -347,13 +348,9 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
 template <typename GT, int CG, bool EXACT, bool GRAY = false>
 static cudaError_t launch_bwd_tt(const CropParams &p, const CUtensorMap &gx_map, unsigned ctas, unsigned cs, size_t smem, cudaStream_t s)
 {
-    if (smem > 48 * 1024) {
-        static size_t granted = 0;                 // per template instance; only ever grows
-        if (smem > granted) {
-            cudaError_t e = cudaFuncSetAttribute(stn_bwd_kernel<GT, CG, EXACT, GRAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            granted = smem;
-        }
+    {
+        const cudaError_t e = grant_dynamic_smem(reinterpret_cast<const void *>(&stn_bwd_kernel<GT, CG, EXACT, GRAY>), smem);
+        if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -420,7 +417,7 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     // (the theta-only kernel of gx == NULL has the machine to itself: up to 8 CTAs per crop)
     const bool theta_only = !p.gx && theta_only_kernel_enabled();
     const unsigned cs_max = theta_only ? 8 : STN_THETA_CS_MAX;
-    while (cs < cs_max && (long long)p.N * cs < 2LL * kNumSMs && npx / (2 * cs) >= kThreads / 2) cs *= 2;
+    while (cs < cs_max && (long long)p.N * cs < 2LL * num_sms() && npx / (2 * cs) >= kThreads / 2) cs *= 2;
     p.ctas_per_crop = (int)cs;
     p.px_per_cta = (int)((npx + cs - 1) / cs);
     const long long theta_ctas = (long long)p.N * cs;
@@ -451,11 +448,11 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
 #endif
         {
             const long long all_tiles = (long long)(p.N / p.K) * p.gx_tiles_per_frame;
-            long long tpw = all_tiles / ((long long)kWarps * kNumSMs * 6 * p.K);     // K crops per frame: K times the work per tile
+            long long tpw = all_tiles / ((long long)kWarps * num_sms() * 6 * p.K);     // K crops per frame: K times the work per tile
             if (tpw < 1) tpw = 1;
             // several crops per frame: the per-CTA prologue derives K geometries -- three tiles per warp amortise it
             // (cfg4: 541 vs 561 us with one, 545 with two, 601 with eight)
-            if (p.K > 1 && tpw < 3 && all_tiles >= 3LL * kWarps * 4 * kNumSMs) tpw = 3;
+            if (p.K > 1 && tpw < 3 && all_tiles >= 3LL * kWarps * 4 * num_sms()) tpw = 3;
             if (tpw > STN_GX_MAX_TILES_PER_WARP) tpw = STN_GX_MAX_TILES_PER_WARP;
             if (gx_tiles_per_warp_override() > 0) tpw = gx_tiles_per_warp_override();
             p.gx_tiles_per_warp = (int)tpw;
@@ -491,6 +488,7 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         e = gy_dtype == 0 ? launch_bwd_t<float>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream)
                           : launch_bwd_t<__nv_bfloat16>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream);
     count_launch();
+    note_kernel(!p.gx && theta_only_kernel_enabled() ? "stn_bwd_theta_kernel" : "stn_bwd_kernel");
     if (e != cudaSuccess) return set_error("crop_bwd launch failed: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -58,7 +58,7 @@ int launch_prepare_images(const float *x, float *out, float scale, int b, int h,
     // four items per thread where the plane is big enough; about 16 CTAs per SM in total, grid-stride beyond
     int gx = (plane4 + 4 * kThreads - 1) / (4 * kThreads);
     int gy = (int)(planes < 65535 ? planes : 65535);
-    const long long want = 16LL * kNumSMs;
+    const long long want = 16LL * num_sms();
     if ((long long)gx * gy > want) {
         gx = (int)((want + gy - 1) / gy);
         if (gx < 1) gx = 1;
@@ -72,6 +72,7 @@ int launch_prepare_images(const float *x, float *out, float scale, int b, int h,
     cfg.numAttrs = fill_launch_attrs(attr, 0);
     cudaError_t e = cudaLaunchKernelEx(&cfg, prepare_images_kernel, x, out, scale, plane4, (int)planes, vec);
     count_launch();
+    note_kernel("prepare_images_kernel");
     if (e != cudaSuccess) return set_error("prepare_images launch failed: %s", cudaGetErrorString(e));
     return 0;
 }

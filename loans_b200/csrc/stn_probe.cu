@@ -1,0 +1,78 @@
+// stn_probe.cu -- measurement aids for bench.py's "floor" block (declared in include/loans_stn_devel.h; no operator uses
+// them).  What does a kernel of this SHAPE cost on this GPU before any STN arithmetic is done?
+//   mode 0  empty:   griddepcontrol.launch_dependents; griddepcontrol.wait; exit -- the launch / programmatic-dependent-
+//                    launch cost of one graph node with our launch attributes;
+//   mode 1  chain:   per CTA one 4-byte load (as theta), then per thread one load whose address depends on it (as the
+//                    taps), then one store (as the crop): the two dependent DRAM round trips every fused kernel has;
+//   mode 2  stream:  in_bytes read and out_bytes written as plain coalesced 16-byte accesses, nothing else: the same
+//                    algorithmic bytes as a fused launch, moved by the simplest possible kernel of the same grid.
+#include "../../include/loans_stn_devel.h"
+#include "stn_common.cuh"
+
+namespace stn {
+
+__global__ void __launch_bounds__(kThreads) probe_empty_kernel()
+{
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
+__global__ void __launch_bounds__(kThreads) probe_chain_kernel(const int *in, float *out, long long in_elems)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    // hop 1: one word per CTA, a different 128-byte line each (in[] holds small offsets)
+    const long long slot = ((long long)blockIdx.x * 32) % in_elems;
+    const int off = __ldg(in + slot);
+    // hop 2: one word per thread, 32-byte sectors apart (the stride of down-sampled taps), address depends on hop 1
+    const long long at = (slot + 8LL * threadIdx.x + (long long)(off & 1023) * 4096 + 2048) % in_elems;
+    const float v = __int_as_float(__ldg(in + at));
+    out[(long long)blockIdx.x * kThreads + threadIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) probe_stream_kernel(const float4 *in, float4 *out, long long n_in, long long n_out)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * kThreads, t0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = t0; i < n_in; i += stride) {
+        const float4 v = __ldg(in + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x == 1.2345e38f) acc.y = 1.f;                     // keeps the loads alive; never true for the probe's inputs
+    const float4 z = make_float4(0.f, 0.f, acc.y * 0.f, 0.f);
+    for (long long i = t0; i < n_out; i += stride) out[i] = z;
+}
+
+}  // namespace stn
+
+using namespace stn;
+
+extern "C" int loans_stn_probe(int mode, const void *in, void *out, long long in_bytes, long long out_bytes, int ctas, void *stream)
+{
+    if (ctas < 1 || in_bytes < 0 || out_bytes < 0) return set_error("loans_stn_probe: bad arguments");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, 0);
+    cudaError_t e;
+    if (mode == 0) {
+        e = cudaLaunchKernelEx(&cfg, probe_empty_kernel);
+    } else if (mode == 1) {
+        if (!in || !out || in_bytes < (1 << 20) || out_bytes < 4LL * ctas * kThreads)
+            return set_error("loans_stn_probe: chain mode needs >= 1 MiB of input and 4*ctas*256 bytes of output");
+        e = cudaLaunchKernelEx(&cfg, probe_chain_kernel, (const int *)in, (float *)out, in_bytes / 4);
+    } else if (mode == 2) {
+        if ((in_bytes && !in) || (out_bytes && !out)) return set_error("loans_stn_probe: NULL buffer");
+        e = cudaLaunchKernelEx(&cfg, probe_stream_kernel, (const float4 *)in, (float4 *)out, in_bytes / 16, out_bytes / 16);
+    } else {
+        return set_error("loans_stn_probe: unknown mode %d", mode);
+    }
+    count_launch();
+    if (e != cudaSuccess) return set_error("loans_stn_probe launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -190,7 +190,7 @@ int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream)
     if (rows > 16) rows = 16;
     if (rows > p.oH) rows = p.oH;
     // do not starve the machine: at least ~2 CTAs per SM when the batch is small
-    while (rows > 1 && (long long)p.N * ((p.oH + rows - 1) / rows) < 2LL * kNumSMs) rows = (rows + 1) / 2;
+    while (rows > 1 && (long long)p.N * ((p.oH + rows - 1) / rows) < 2LL * num_sms()) rows = (rows + 1) / 2;
     p.sep_rows = rows;
     p.sep_pitch = pitch;
     p.ctas_per_crop = (p.oH + rows - 1) / rows;
@@ -201,18 +201,13 @@ int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream)
     const long long ctas = (long long)p.N * p.ctas_per_crop;
     if (ctas > 0x7fffffffLL) return set_error("sep_fwd: too many CTAs (%lld)", ctas);
     cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) {
-        static size_t granted[2] = {0, 0};
-        if (smem > granted[y_dtype]) {
-            e = y_dtype == 0 ? cudaFuncSetAttribute(stn_sep_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(stn_sep_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return set_error("sep_fwd: cannot get %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-            granted[y_dtype] = smem;
-        }
-    }
+    e = y_dtype == 0 ? grant_dynamic_smem(reinterpret_cast<const void *>(&stn_sep_fwd_kernel<float>), smem)
+                     : grant_dynamic_smem(reinterpret_cast<const void *>(&stn_sep_fwd_kernel<__nv_bfloat16>), smem);
+    if (e != cudaSuccess) return set_error("sep_fwd: cannot get %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     if (y_dtype == 0) stn_sep_fwd_kernel<float><<<(unsigned)ctas, kThreads, smem, stream>>>(p);
     else stn_sep_fwd_kernel<__nv_bfloat16><<<(unsigned)ctas, kThreads, smem, stream>>>(p);
     count_launch();
+    note_kernel("stn_sep_fwd_kernel");
     return check_launch("sep_fwd");
 }
 

@@ -25,6 +25,7 @@ int launch_rotation_dropout(const float *in, float mask01, float *out, int n, cu
     const int n6 = n * 6;
     rotation_dropout_kernel<<<(n6 + kThreads - 1) / kThreads, kThreads, 0, stream>>>(in, mask01, out, n6);
     count_launch();
+    note_kernel("rotation_dropout_kernel");
     return check_launch("rotation_dropout");
 }
 
@@ -57,6 +58,7 @@ int launch_grid_fwd(const float *theta, float *grid, int n, int oh, int ow, cuda
     grid_fwd_kernel<<<(unsigned)((long long)n * cpc), kThreads, sizeof(float) * (ow + oh), stream>>>(
         theta, grid, n, oh, ow, xstep, ystep, cpc, px_per_cta);
     count_launch();
+    note_kernel("grid_fwd_kernel");
     return check_launch("grid_fwd");
 }
 
@@ -102,6 +104,7 @@ int launch_grid_bwd(const float *ggrid, float *gtheta, int n, int oh, int ow, cu
     const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
     grid_bwd_kernel<<<(unsigned)(2 * n), kThreads, sizeof(float) * (ow + oh), stream>>>(ggrid, gtheta, oh, ow, xstep, ystep);
     count_launch();
+    note_kernel("grid_bwd_kernel");
     return check_launch("grid_bwd");
 }
 
@@ -222,6 +225,7 @@ int launch_sampler_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
         else sampler_bwd_kernel<__nv_bfloat16, 4><<<grid, kThreads, 0, stream>>>(p);
     }
     count_launch();
+    note_kernel("sampler_bwd_kernel");
     return check_launch("sampler_bwd");
 }
 

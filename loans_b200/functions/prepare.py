@@ -9,7 +9,7 @@ no host round trip, no CPU fallback.
 import torch
 
 from loans_b200 import _lib
-from loans_b200.functions.spatial_transformer import InvalidType, _expect, _need_cuda, _ptr, _stream
+from loans_b200.functions.spatial_transformer import InvalidType, _expect, _need_cuda, _on_device, _ptr, _stream, resolve
 
 
 def prepare_images(images, scale=1.0):
@@ -19,13 +19,14 @@ def prepare_images(images, scale=1.0):
     ``scale=255``: ``images`` is the raw [0,1] frame batch; the multiply is folded into the kernel.
     The result carries no gradient, as in the reference (it rebuilds the arrays on the host).
     """
+    images = resolve(images)
     _need_cuda(images)
     _expect(images.dtype == torch.float32, "images.dtype.char == 'f' (got %s)" % images.dtype)
     _expect(images.dim() == 4 and images.shape[1] == 3, "images.shape == (B, 3, H, W) (got %s)" % (tuple(images.shape),))
     x = images.detach().contiguous()
     b, c, h, w = x.shape
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x):
         _lib.check(_lib.lib().loans_stn_prepare_images(_ptr(x), float(scale), _ptr(out), b, c, h, w, _stream()),
                    "loans_stn_prepare_images")
     return out

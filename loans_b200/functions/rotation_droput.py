@@ -12,7 +12,8 @@ import torch
 
 from loans_b200 import _lib
 from loans_b200.configuration import config
-from loans_b200.functions.spatial_transformer import InvalidType, _need_cuda, _ptr, _stream
+from loans_b200.functions.spatial_transformer import (Deferred, InvalidType, _modified_error, _need_cuda, _on_device, _ptr,
+                                                       _stream, _unchanged, resolve)
 
 
 def draw_mask_value(ratio):
@@ -27,7 +28,7 @@ class _RotationDropoutFn(torch.autograd.Function):
     def forward(ctx, x, mask_value, can_backprop):
         x = x.contiguous()
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             _lib.check(_lib.lib().loans_stn_rotation_dropout(_ptr(x), mask_value, _ptr(y), x.shape[0], _stream()),
                        "loans_stn_rotation_dropout")
         ctx.meta = (mask_value, can_backprop)
@@ -42,7 +43,7 @@ class _RotationDropoutFn(torch.autograd.Function):
                                  "(backward after a test-mode forward, as in the reference)")
         gy = gy.contiguous()
         gx = torch.empty_like(gy)
-        with torch.cuda.device(gy.device):
+        with _on_device(gy):
             _lib.check(_lib.lib().loans_stn_rotation_dropout(_ptr(gy), mask_value, _ptr(gx), gy.shape[0], _stream()),
                        "loans_stn_rotation_dropout")
         return gx, None, None
@@ -65,13 +66,28 @@ class RotationDropout(object):
             raise InvalidType("loans_b200 computes this path in float32 (got %s)" % x.dtype)
 
     def __call__(self, x):
+        x = resolve(x)
         self.check_type_forward(x)
         _need_cuda(x)
-        if not config.train:
-            return _RotationDropoutFn.apply(x, float(self.dropout_ratio), False)
-        if not hasattr(self, "mask_value"):
-            self.mask_value = draw_mask_value(self.dropout_ratio)
-        return _RotationDropoutFn.apply(x, self.mask_value, True)
+        train = bool(config.train)
+        if train:
+            if not hasattr(self, "mask_value"):
+                self.mask_value = draw_mask_value(self.dropout_ratio)       # one draw per call for the whole batch (:41)
+            value = self.mask_value
+        else:
+            value = float(self.dropout_ratio)                               # :33-35
+        if not config.defer:
+            return _RotationDropoutFn.apply(x, value, train)
+        # deferred: the grid node that normally follows hands (x, value) to the fused kernel and this multiply is never
+        # launched on its own; anything else that touches the result materialises it with loans_stn_rotation_dropout
+        note = {"theta": x, "theta_version": x._version, "theta_ptr": x.data_ptr(), "mask01": value, "can_backprop": train}
+
+        def materialise():
+            if not _unchanged(x, note["theta_version"], note["theta_ptr"]):
+                raise _modified_error("the input of rotation_dropout")
+            return _RotationDropoutFn.apply(x, value, train)
+
+        return Deferred(x.shape, x.dtype, x.device, x.requires_grad, materialise, ("rotation_dropout", note))
 
 
 def rotation_dropout(x, ratio=.5, **kwargs):

@@ -369,3 +369,175 @@ def test_grayscale_epilogue_on_degenerate_transforms(T):
             gt0, gx0, _ = oc.crop_backward(x, thetas, osz, on.grayscale_backward(gg), None, mask, 1)
             assert np.abs(tt.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
             assert np.abs(xt.grad.cpu().numpy() - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())
+
+
+# ------------------------------------------------------------------------------------------------ round 2: deferral
+def _corner_loss(points):
+    return points[:, :, 0, 0].sum() * 0.5 + points[:, :, 0, -1].sum() * 0.25 - points[:, :, -1, 0].sum()
+
+
+@pytest.mark.parametrize("grad_x", [False, True])
+def test_three_reference_calls_are_two_launches_and_bitwise_the_fused_call(T, grad_x):
+    """sheep/sheep_localizer.py:61-63 written out, with the corner regularisers' use of `points`
+    (common/utils.py:152-157): ONE forward and ONE backward kernel, the ones stn_crop launches, same bits."""
+    from loans_b200 import _lib
+    from loans_b200.functions import rotation_dropout, spatial_transformer_grid, spatial_transformer_sampler, stn_crop
+    wl = W.WORKLOADS["cfg2"]
+    d = W.make_inputs(wl, batch=64, rotate=True)             # 64 crops: the automatic rule takes row bands when gx is wanted
+    osz = (wl.out_h, wl.out_w)
+    gy = _t(T, d["gy"])
+
+    def run(three_calls):
+        images = _t(T, d["x"], grad=grad_x)
+        theta = _t(T, d["theta"].reshape(-1, 6), grad=True)
+        n0 = _lib.launch_count()
+        if three_calls:
+            tp = rotation_dropout(theta.reshape(-1, 2, 3), ratio=0.0)
+            points = spatial_transformer_grid(tp, osz)
+            rois = spatial_transformer_sampler(images, points)
+        else:
+            rois, points = stn_crop(images, theta.reshape(-1, 2, 3), osz, ratio=0.0)
+        fwd_kernel = _lib.last_kernel()
+        n1 = _lib.launch_count()
+        loss = (rois * gy).sum() + _corner_loss(points)      # torch's own kernels from here on: not counted
+        loss.backward()
+        T.cuda.synchronize()
+        return (rois.detach(), points.detach(), theta.grad, images.grad, n1 - n0, _lib.launch_count() - n1, fwd_kernel,
+                _lib.last_kernel())
+
+    a, b = run(True), run(False)
+    assert a[4] == 1 and a[5] == 1 and b[4] == 1 and b[5] == 1
+    assert a[6] == b[6] == "stn_fwd_kernel"
+    assert a[7] == b[7] == ("stn_bwd_band_kernel/row" if grad_x else "stn_bwd_theta_tab_kernel")
+    for u, v in zip(a[:4], b[:4]):
+        assert (u is None and v is None) or T.equal(u, v)
+    gg = np.zeros((64, 2) + osz, np.float32)
+    gg[:, :, 0, 0], gg[:, :, 0, -1], gg[:, :, -1, 0] = 0.5, 0.25, -1.0
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], gg, 0.0)
+    assert np.array_equal(a[0].cpu().numpy(), y0) and np.array_equal(a[1].cpu().numpy(), grid0)
+    assert np.abs(a[2].cpu().numpy().reshape(-1, 2, 3) - gt0).max() <= 1e-4 * np.abs(gt0).max()
+    if grad_x:
+        assert np.abs(a[3].cpu().numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max()
+
+
+def test_materialised_intermediates_give_the_same_numbers(T):
+    """Looking at the masked theta or at the grid between the calls materialises them with their own kernels; the sampler then
+    takes the gradient through `points` (hooks see it).  Same crops, same grid, gradients within the bars."""
+    import loans_b200
+    from loans_b200 import _lib
+    from loans_b200.functions import rotation_dropout, spatial_transformer_grid, spatial_transformer_sampler
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=8, rotate=True)
+    osz = (wl.out_h, wl.out_w)
+    gy = _t(T, d["gy"])
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+    gg = np.zeros((8, 2) + osz, np.float32)
+    gg[:, :, 0, 0], gg[:, :, 0, -1], gg[:, :, -1, 0] = 0.5, 0.25, -1.0
+    gt0, gx0, ggrid0 = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], gg, 0.0)
+    for mode in ("touch_theta", "touch_grid", "eager"):
+        images = _t(T, d["x"], grad=True)
+        theta = _t(T, d["theta"], grad=True)
+        seen = []
+        with loans_b200.using_config("defer", mode != "eager"):
+            tp = rotation_dropout(theta, ratio=0.0)
+            if mode == "touch_theta":
+                assert float(tp[:, 0, 1].abs().max()) == 0.0
+            points = spatial_transformer_grid(tp, osz)
+            if mode == "touch_grid":
+                points.register_hook(lambda g: seen.append(g.detach().clone()))
+            rois = spatial_transformer_sampler(images, points)
+        if mode == "touch_grid":
+            assert _lib.last_kernel() == "stn_fwd_kernel"              # sampled from theta in registers, grid not re-read
+        ((rois * gy).sum() + _corner_loss(points)).backward()
+        assert np.array_equal(rois.detach().cpu().numpy(), y0), mode
+        assert np.array_equal(points.detach().cpu().numpy(), grid0), mode
+        assert np.abs(theta.grad.cpu().numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max(), mode
+        assert np.abs(images.grad.cpu().numpy() - gx0).max() <= 1e-5 * np.abs(gx0).max(), mode
+        if mode == "touch_grid":
+            assert len(seen) == 1 and np.array_equal(seen[0].cpu().numpy(), ggrid0 + gg)   # per-pixel grid gradient + the corners'
+
+
+def test_grid_data_edit_between_the_calls_is_sampled_as_edited(T):
+    from loans_b200.functions import spatial_transformer_grid, spatial_transformer_sampler
+    rng = np.random.default_rng(4)
+    x = rng.random((3, 3, 20, 20), dtype=np.float32)
+    theta = W.make_theta(rng, 3)
+    g0 = oc.grid_forward(theta, (7, 7)) * np.float32(0.5)
+    for edit in ("data", "inplace"):
+        grid = spatial_transformer_grid(_t(T, theta), (7, 7))
+        if edit == "data":
+            grid.data[...] *= 0.5                              # does not move the version counter
+        else:
+            grid.mul_(0.5)
+        y = spatial_transformer_sampler(_t(T, x), grid)
+        assert np.array_equal(y.cpu().numpy(), oc.sampler_forward(x, g0)), edit
+    th = _t(T, theta)
+    grid = spatial_transformer_grid(th, (7, 7))
+    th.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        spatial_transformer_sampler(_t(T, x), grid)
+
+
+def test_upright_hint_takes_the_axis_aligned_kernels_on_a_pre_masked_theta(T):
+    """mask01 = 1 with a theta whose rotation terms are already zero (the materialised output of rotation_dropout): with
+    LOANS_STN_FLAG_UPRIGHT the backward takes the band / table kernels and gives the bits of the mask01 = 0 call; a rotated
+    crop among them is found on the device and handled by the general roles inside the same launch."""
+    from tests import gpu_util as G
+    from loans_b200 import _lib
+    wl = W.WORKLOADS["cfg2"]
+    d = W.make_inputs(wl, batch=64, rotate=True)
+    masked = d["theta"].copy()
+    masked[:, 0, 1] = 0
+    masked[:, 1, 0] = 0
+    osz = (wl.out_h, wl.out_w)
+    L = _lib.lib()
+    xd, gyd = G.dev(d["x"]), G.dev(d["gy"])
+    n = 64
+
+    def bwd(theta, mask, flags, need_gx=True):
+        td = G.dev(theta)
+        gt = T.empty((n, 2, 3), device="cuda")
+        gx = T.empty_like(xd) if need_gx else None
+        _lib.check(L.loans_stn_crop_bwd_ex(G.ptr(xd), G.ptr(td), float(mask), G.ptr(gyd), None, None, G.ptr(gt), G.ptr(gx), None, flags,
+                                           n, 1, 3, wl.height, wl.width, osz[0], osz[1], _lib.F32, G.stream()), "bwd_ex")
+        T.cuda.synchronize()
+        return gt.cpu().numpy(), (None if gx is None else gx.cpu().numpy()), _lib.last_kernel()
+
+    for need_gx, kernel in ((True, "stn_bwd_band_kernel/row"), (False, "stn_bwd_theta_tab_kernel")):
+        gt_a, gx_a, k_a = bwd(d["theta"], 0.0, 0, need_gx)
+        gt_b, gx_b, k_b = bwd(masked, 1.0, _lib.FLAG_UPRIGHT, need_gx)
+        gt_c, gx_c, k_c = bwd(masked, 1.0, 0, need_gx)
+        assert k_a == k_b == kernel and k_c in ("stn_bwd_kernel", "stn_bwd_theta_kernel")
+        if need_gx:
+            assert np.array_equal(gx_a, gx_b) and G.rel_max(gx_c, gx_a) <= 2e-6
+        # d/d(theta01), d/d(theta10) are not masked when mask01 = 1: compare the four entries both calls define alike
+        keep = np.array([[1, 0, 1], [0, 1, 1]], bool)
+        assert np.array_equal(gt_a[:, keep], gt_b[:, keep]) and G.rel_max(gt_c, gt_b) <= 1e-4
+        # a wrong hint: some crops ARE rotated -- still the oracle's numbers
+        mixed = masked.copy()
+        mixed[::3] = d["theta"][::3]
+        gt_m, gx_m, k_m = bwd(mixed, 1.0, _lib.FLAG_UPRIGHT, need_gx)
+        assert k_m == kernel
+        gt0, gx0, _ = oc.crop_backward(d["x"], mixed, osz, d["gy"], None, 1.0)
+        assert G.rel_max(gt_m, gt0) <= 1e-4
+        if need_gx:
+            assert G.rel_max(gx_m, gx0) <= 2e-6
+
+
+def test_same_kernel_on_a_second_device_in_one_process(T):
+    """The opt-in to > 48 KiB of dynamic shared memory is per device: the backward must work on cuda:1 after cuda:0."""
+    if T.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from loans_b200.functions import stn_crop
+    wl = W.WORKLOADS["cfg1"]
+    d = W.make_inputs(wl, batch=4)
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], (75, 75), d["gy"], None, 0.0)
+    for dev in ("cuda:0", "cuda:1"):
+        x = T.from_numpy(d["x"]).to(dev).requires_grad_()
+        th = T.from_numpy(d["theta"]).to(dev).requires_grad_()
+        rois, _ = stn_crop(x, th, (75, 75), ratio=0.0)
+        rois.backward(T.from_numpy(d["gy"]).to(dev))
+        T.cuda.synchronize(dev)
+        assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max(), dev
+        assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max(), dev

@@ -202,7 +202,8 @@ def test_golden_fixture_on_device(G):
 
 @pytest.mark.parametrize("name,batch", [("cfg1", None), ("cfg2", 16), ("cfg3", 6), ("cfg4", 3)])
 def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
-    """LOANS_STN_CFG_TMA_FORWARD routes axis-aligned crops (mask01 == 0) through the table + TMA-staged forward."""
+    """The kernels written for axis-aligned crops (mask01 == 0: band / table-driven backward, and in a -DSTN_DEVEL build the
+    TMA-staged forward) against the general kernels (LOANS_STN_CFG_FORCE_GENERAL) on the same inputs."""
     from loans_b200 import _lib
     wl = W.WORKLOADS[name]
     d = W.make_inputs(wl, batch=batch, rotate=True, with_ggrid=True)
@@ -210,15 +211,24 @@ def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
     d["theta"][1::7, 0, 0] *= -1.0                    # mirrored crops
     osz = (wl.out_h, wl.out_w)
     k = wl.crops_per_frame
-    y0, g0 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
-    b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
-    n0 = _lib.launch_count()
     try:
-        _lib.tma_forward(True)
-        y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
-        b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+        _lib.force_general(True)
+        y0, g0 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+        b0 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+        assert _lib.last_kernel() == "stn_bwd_kernel"
     finally:
-        _lib.tma_forward(False)
+        _lib.force_general(False)
+    n0 = _lib.launch_count()
+    devel = _lib.lib().loans_stn_configure(_lib.CFG_TMA_FORWARD, 1) == 0
+    try:
+        y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
+        _lib.band_backward(True)
+        b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+        assert _lib.last_kernel() in ("stn_bwd_band_kernel/row", "stn_bwd_band_kernel/cta", "stn_bwd_kframe_kernel")
+    finally:
+        _lib.band_backward(None)
+        if devel:
+            _lib.tma_forward(False)
     assert _lib.launch_count() - n0 == 2
     assert np.array_equal(y0, y1) and np.array_equal(g0, g1)
     assert np.array_equal(b0[2], b1[2])                                   # ggrid bit-exact
@@ -236,11 +246,14 @@ def test_axis_aligned_kernels_on_ragged_shapes(G, shape):
                       [[40.0, 3.0, 0.5], [-2.0, 55.0, 0.1]]], np.float32)
     x = rng.random((len(theta), c, h, w), dtype=np.float32)
     from loans_b200 import _lib
+    devel = _lib.lib().loans_stn_configure(_lib.CFG_TMA_FORWARD, 1) == 0      # the TMA-staged forward too, where it is built in
     try:
-        _lib.tma_forward(True)
+        _lib.band_backward(True)
         _full_check(G, x, theta, (oh, ow), 0.0, 1, seed=7)
     finally:
-        _lib.tma_forward(False)
+        _lib.band_backward(None)
+        if devel:
+            _lib.tma_forward(False)
 
 
 # ------------------------------------------------------------------------------------------------ band backward
