@@ -12,7 +12,7 @@ def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
-                          "--steps", "2", "--warmup", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+                          "--steps", "2", "--warmup", "1", "--ref-tasks", "2"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip()
 
@@ -26,8 +26,15 @@ def test_reference_arm_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    # crops per step / time per step is the value: 4 frames of cfg1 per step
-    assert abs(line["value"] - 4 / (line["ms_per_step"] * 1e-3)) / line["value"] < 1e-6
+    # crops per step / time per step is the value: 2 tasks per core and step, a task = one 2-frame shard of cfg1
+    crops = (os.cpu_count() or 1) * 2 * 2
+    assert cb["cores"] == (os.cpu_count() or 1)
+    assert abs(line["value"] - crops / (line["ms_per_step"] * 1e-3)) / line["value"] < 1e-6
+    # the two arms name the workload with the same keys (the driver compares the config dicts)
+    sys.path.insert(0, ROOT)
+    import bench
+    from loans_b200 import workloads as W
+    assert set(line["config"]) == set(bench.workload_config(W.WORKLOADS["cfg2"], True))
 
 
 def test_reference_arm_other_ranks_print_nothing():
