@@ -1,5 +1,5 @@
 """A/B of two builds of libloans_stn.so on the same GPU, interleaved: times loans_stn_crop_fwd / _bwd (CUDA-graph replay over
-rotating buffer sets).  usage: so_ab.py <a.so> <b.so> [cfg2 cfg5 ...]"""
+rotating buffer sets).  usage: so_ab.py <a.so> <b.so> [<c.so> ...] [cfg2 cfg5 ...]"""
 import ctypes
 import json
 import math
@@ -42,8 +42,8 @@ def graph_time(fn, sets, reps):
 
 
 def main():
-    libs = [(p, load(p)) for p in sys.argv[1:3]]
-    names = sys.argv[3:] or ["cfg2", "cfg5"]
+    libs = [(p, load(p)) for p in sys.argv[1:] if p.endswith(".so")]
+    names = [a for a in sys.argv[1:] if not a.endswith(".so")] or ["cfg2", "cfg5"]
     dev = torch.device("cuda", 0)
     for name in names:
         wl = W.WORKLOADS[name]._replace(rotation_ratio=0.0)
