@@ -93,7 +93,6 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 #ifdef STN_DEVEL
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
 #endif
-int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not taken
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement);   // -1: use the general kernel
 void band_tuning(int which, int value);
 int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not taken
@@ -178,11 +177,9 @@ static int crop_bwd_dispatch(const CropParams &p, bool upright, int gy_dtype, cu
             const int rc = launch_crop_bwd_band(p, gy_dtype, stream, band < 0);
             if (rc >= 0) return rc;
         }
-        // several crops per frame, gx wanted: frame-row tiles gathered from per-crop tables (stn_kframe.cu)
-        if (p.gx != nullptr && p.K > 1) {
-            const int rc = launch_crop_bwd_kframe(p, gy_dtype, stream);
-            if (rc >= 0) return rc;
-        }
+        // several crops per frame with gx wanted stay with the general kernel: three axis-aligned designs for that case
+        // (warp-owned frame-row windows, a per-window work queue, CTA-owned bands with crop-sequential phases) all measured
+        // slower than it at BASELINE config 4 (profiles/README.md, round 2)
     }
     return launch_crop_bwd(p, gy_dtype, stream);
 }
