@@ -803,6 +803,32 @@ def run_ours(args):
                                               "what": "fwd+bwd with the localizer's grayscale epilogue fused (1-channel crops "
                                                       "and gy) and corner points"}
 
+        if C == 3:
+            # conv-ready crops (8f rank 3): bf16, planar vs channels-last padded to four channels, same work otherwise
+            ycl = torch.empty((N, oH, oW, 4), dtype=torch.bfloat16, device=dev)
+            gycl = torch.randn((N, oH, oW, 4), dtype=torch.float32, device=dev).to(torch.bfloat16)
+            ypl = torch.empty((N, C, oH, oW), dtype=torch.bfloat16, device=dev)
+            gypl = gycl[..., :3].permute(0, 3, 1, 2).contiguous()
+
+            def step_bf16(e, flags):
+                st = torch.cuda.current_stream().cuda_stream
+                nh = flags == _lib.FLAG_NHWC4
+                _lib.check(L.loans_stn_crop_fwd_ex(ptr(e["x"]), ptr(e["theta"]), float(mask01), ptr(ycl if nh else ypl), ptr(e["grid"]), None,
+                                                   flags, N, K, C, H, Wd, oH, oW, _lib.BF16, st), "crop_fwd_ex")
+                _lib.check(L.loans_stn_crop_bwd_ex(ptr(e["x"]), ptr(e["theta"]), float(mask01), ptr(gycl if nh else gypl), None, None,
+                                                   ptr(e["gtheta"]), ptr(e["gx"]), None, flags, N, K, C, H, Wd, oH, oW, _lib.BF16, st), "crop_bwd_ex")
+            res = {}
+            for key, flags in (("nchw", 0), ("nhwc4", _lib.FLAG_NHWC4)):
+                step_bf16(sets[0], flags)
+                g_b = hz.capture(lambda flags=flags: [step_bf16(e, flags) for e in sets])
+                for _ in range(3):
+                    g_b.replay()
+                res[key] = pb.per_launch(g_b, steps) * 1e3
+            next_rows["bf16_crops_channels_last"] = {"us_per_step_nchw": res["nchw"], "us_per_step_nhwc4": res["nhwc4"],
+                                                     "value": world * N / (res["nhwc4"] * 1e-6), "unit": UNIT,
+                                                     "what": "fwd+bwd with bf16 crops and gy: planar (N,C,oH,oW) vs channels-last padded to "
+                                                             "four channels (N,oH,oW,4), the layout the assessor's first convolution consumes"}
+
     # ---- the reference's GPU path on the same inputs: cuDNN's spatial-transformer kernels (what chainer calls on a GPU)
     gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cudnn and K == 1 and not bf16 and need_gx:

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         const int r0 = rank * p.band_rows_cta, r1 = min(p.oH, r0 + p.band_rows_cta);
         const int row_elems = max(r1 - r0, 0) * p.oW;
         const int lines = (row_elems * (int)sizeof(GT) + 127) / 128;
-        constexpr int gplanes = GRAY ? 1 : CG;
+        constexpr int gplanes = crop_planes<GT, GRAY>(CG);
         for (int e = tid; e < lines * gplanes; e += kThreads) {
             const int ch = e / lines, l = e - ch * lines;
             const char *a = reinterpret_cast<const char *>(reinterpret_cast<const GT *>(p.gy) + ((size_t)n * gplanes + ch) * p.oH * p.oW +
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
     const int plane = H * W;
     const size_t fpx = (size_t)plane;
     const float *xb = p.x + (size_t)n * CG * fpx;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : CG) * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * crop_planes<GT, GRAY>(CG) * npx;
     float *gxb = p.gx + (size_t)n * CG * fpx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 4) stn_bwd_theta_tab_kernel(const __
     __syncthreads();
     const int npx = oH * oW, plane = H * W;
     const float *xb = p.x + (size_t)(n / p.K) * CG * plane;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : CG) * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * crop_planes<GT, GRAY>(CG) * npx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
     float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -626,7 +626,9 @@ int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream)
     const long long ctas = (long long)p.N * cs;
     if (ctas > 0x7fffffffLL) return -1;
     cudaError_t e;
-    if (gy_dtype == 0)
+    if (p.nhwc)
+        e = launch_theta_tab_tt<Nhwc4, 3, false>(p, (unsigned)ctas, cs, smem, stream);
+    else if (gy_dtype == 0)
         e = p.C == 1 ? launch_theta_tab_tt<float, 1, false>(p, (unsigned)ctas, cs, smem, stream)
           : p.C == 4 ? launch_theta_tab_tt<float, 4, false>(p, (unsigned)ctas, cs, smem, stream)
           : p.gray   ? launch_theta_tab_tt<float, 3, true>(p, (unsigned)ctas, cs, smem, stream)
@@ -802,7 +804,10 @@ int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool b
     if (ctas > 0x7fffffffLL) return -1;
     const int kind = rowband ? 3 : (knob == 2 ? 2 : 1);
     cudaError_t e;
-    if (gy_dtype == 0)
+    if (p.nhwc)
+        e = kind == 3 ? launch_band_ttt<Nhwc4, 3, 1, 4, false, true>(p, (unsigned)ctas, cs, smem, stream)
+                      : launch_band_ttt<Nhwc4, 3, 1, 4, false, false>(p, (unsigned)ctas, cs, smem, stream);
+    else if (gy_dtype == 0)
         e = p.C == 1 ? launch_band_tt<float, 1>(p, (unsigned)ctas, cs, smem, stream, kind)
           : p.C == 3 ? launch_band_tt<float, 3>(p, (unsigned)ctas, cs, smem, stream, kind)
                      : launch_band_tt<float, 4>(p, (unsigned)ctas, cs, smem, stream, kind);

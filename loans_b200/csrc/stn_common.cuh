@@ -58,6 +58,17 @@ struct CropParams {
     int band_fb_tiles_per_warp;                                 // declined crops: tiles per warp in the general gx role
 };
 
+// Channels-last crop pixel with the channel count padded to four (LOANS_STN_FLAG_NHWC4: c == 3, bf16): y / gy are
+// (N, oH, oW, 4) bf16, one 8-byte store / load per crop pixel -- the layout a tensor-core first convolution of the assessor
+// consumes (reference common/net.py:15-25 is the consumer).  Used as the crop element type of the kernel templates.
+struct alignas(8) Nhwc4 {
+    __nv_bfloat16 c[4];
+};
+// planes of y / gy per crop, in elements of the crop type: C for planar crops, 1 behind the grayscale epilogue and for Nhwc4
+template <typename T, bool GRAY> __host__ __device__ constexpr int crop_planes(int C) { return GRAY ? 1 : C; }
+template <> __host__ __device__ constexpr int crop_planes<Nhwc4, false>(int) { return 1; }
+template <> __host__ __device__ constexpr int crop_planes<Nhwc4, true>(int) { return 1; }
+
 template <typename T> struct Elem;
 template <> struct Elem<float> {
     static __device__ __forceinline__ float load(const float *p, size_t i) { return __ldg(p + i); }
@@ -71,6 +82,20 @@ template <> struct Elem<__nv_bfloat16> {
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, size_t i, float v)
     {
         p[i] = __float2bfloat16_rn(v);
+    }
+};
+
+template <> struct Elem<Nhwc4> {               // planar accessors are never reached with Nhwc4 crops (C == 3: the EXACT paths)
+    static __device__ __forceinline__ float load(const Nhwc4 *p, size_t i) { return __bfloat162float(p[i].c[0]); }
+    static __device__ __forceinline__ void store(Nhwc4 *, size_t, float) {}
+    // one crop pixel: three channels + a zero, one 8-byte store
+    static __device__ __forceinline__ void store_px(Nhwc4 *p, float c0, float c1, float c2)
+    {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(c0, c1), hi = __floats2bfloat162_rn(c2, 0.0f);
+        uint2 v;
+        v.x = *reinterpret_cast<const unsigned *>(&lo);
+        v.y = *reinterpret_cast<const unsigned *>(&hi);
+        *reinterpret_cast<uint2 *>(p) = v;
     }
 };
 
@@ -91,6 +116,15 @@ __device__ __forceinline__ float load_gy(const GT *base, int ch, int npx)
 {
     if (GRAY) return f_mul(gray_coef(ch), Elem<GT>::load(base, 0));
     return Elem<GT>::load(base, ch * npx);
+}
+// channels-last: base points at the pixel; the 8-byte load is the same for every channel (one LDG.64 after CSE), bf16 ->
+// float32 is a shift
+template <>
+__device__ __forceinline__ float load_gy<Nhwc4, false>(const Nhwc4 *base, int ch, int)
+{
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(base));
+    const unsigned w = ch < 2 ? v.x : v.y;
+    return __uint_as_float((ch & 1) ? (w & 0xffff0000u) : (w << 16));
 }
 
 // xs[0..oW) and ys[0..oH) into shared memory (numpy.linspace(-1,1,n,dtype=float32), see stn_math.cuh)

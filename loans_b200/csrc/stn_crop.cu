@@ -25,6 +25,7 @@
 #include <cuda.h>             // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 #include <cstring>
+#include <type_traits>
 
 #include "stn_common.cuh"
 #include "stn_gx_role.cuh"
@@ -39,6 +40,7 @@ namespace stn {
 // with bf16 crops the same bound measured 3.7 % slower at cfg3, so those keep three CTAs per SM (76 registers)
 template <typename YT> struct FwdMinCtas { static constexpr int value = 4; };
 template <> struct FwdMinCtas<__nv_bfloat16> { static constexpr int value = 3; };
+template <> struct FwdMinCtas<Nhwc4> { static constexpr int value = 3; };
 
 template <typename YT, int CG, bool FROM_GRID, bool EXACT>
 __global__ void __launch_bounds__(kThreads, FwdMinCtas<YT>::value) stn_fwd_kernel(const __grid_constant__ CropParams p)
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(kThreads, FwdMinCtas<YT>::value) stn_fwd_kerne
     if (!FROM_GRID) th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * C * plane;
-    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * (p.gray ? 1 : C) * npx;
+    YT *yb = reinterpret_cast<YT *>(p.y) + (size_t)n * (p.gray ? 1 : crop_planes<YT, false>(C)) * npx;
     float *gout = p.grid_out ? p.grid_out + (size_t)n * 2 * npx : nullptr;
     const float *gin = FROM_GRID ? p.grid_in + (size_t)n * 2 * npx : nullptr;
     if (!FROM_GRID && p.corners_out && tile == 0 && threadIdx.x < 4) {
@@ -113,6 +115,13 @@ __global__ void __launch_bounds__(kThreads, FwdMinCtas<YT>::value) stn_fwd_kerne
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) c[ch] = interp(px.wt, px.v[ch % CG][0], px.v[ch % CG][1], px.v[ch % CG][2], px.v[ch % CG][3]);
                 Elem<YT>::store(yb + px.q, 0, gray_mix(c[0], c[1], c[2]));
+                return;
+            }
+            if constexpr (std::is_same<YT, Nhwc4>::value) {      // channels-last: the pixel's three channels in one 8-byte store
+                float c[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) c[ch] = interp(px.wt, px.v[ch % CG][0], px.v[ch % CG][1], px.v[ch % CG][2], px.v[ch % CG][3]);
+                Elem<Nhwc4>::store_px(yb + px.q, c[0], c[1], c[2]);
                 return;
             }
 #pragma unroll
@@ -333,7 +342,9 @@ int launch_crop_fwd(CropParams p, bool from_grid, int y_dtype, cudaStream_t stre
     const size_t smem = sizeof(float) * (size_t)(p.oW + p.oH);
     const int cgsel = pick_channel_group(p.C);
     cudaError_t e;
-    if (y_dtype == 0)
+    if (p.nhwc)                                            // c == 3, bf16, fused path only (checked by the entry point)
+        e = launch_fwd_tt<Nhwc4, 3, false, true>(p, grid, smem, stream);
+    else if (y_dtype == 0)
         e = from_grid ? launch_fwd_t<float, true>(p, cgsel, grid, smem, stream)
                       : launch_fwd_t<float, false>(p, cgsel, grid, smem, stream);
     else
@@ -482,10 +493,12 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream)
     if (smem > 200 * 1024) return set_error("crop_bwd: %d crops per frame need %zu B of shared memory (max 200 KiB)", p.K, smem);
     cudaError_t e;
     if (!p.gx && theta_only_kernel_enabled())
-        e = gy_dtype == 0 ? launch_theta_t<float>(p, cgsel, (unsigned)ctas, cs, smem, stream)
+        e = p.nhwc ? launch_theta_tt<Nhwc4, 3, true>(p, (unsigned)ctas, cs, smem, stream)
+          : gy_dtype == 0 ? launch_theta_t<float>(p, cgsel, (unsigned)ctas, cs, smem, stream)
                           : launch_theta_t<__nv_bfloat16>(p, cgsel, (unsigned)ctas, cs, smem, stream);
     else
-        e = gy_dtype == 0 ? launch_bwd_t<float>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream)
+        e = p.nhwc ? launch_bwd_tt<Nhwc4, 3, true>(p, gx_map, (unsigned)ctas, cs, smem, stream)
+          : gy_dtype == 0 ? launch_bwd_t<float>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream)
                           : launch_bwd_t<__nv_bfloat16>(p, gx_map, cgsel, (unsigned)ctas, cs, smem, stream);
     count_launch();
     note_kernel(!p.gx && theta_only_kernel_enabled() ? "stn_bwd_theta_kernel" : "stn_bwd_kernel");

@@ -22,6 +22,23 @@ struct GyLoader {
     }
 };
 
+template <>
+struct GyLoader<Nhwc4, false> {                // channels-last: element (channel, pixel) of a crop
+    size_t plane;
+    __device__ __forceinline__ float operator()(const Nhwc4 *p, size_t i) const
+    {
+        const int ch = (int)(i / plane);
+        return __bfloat162float(p[i - (size_t)ch * plane].c[ch]);
+    }
+};
+
+// this crop's gy for channel group c0 (pixel 0): planar (N, C, oH, oW), one gray plane, or channels-last pixels
+template <typename GT, bool GRAY>
+__device__ __forceinline__ const GT *crop_gy(const GT *gy, size_t crop, int C, int c0, int npx)
+{
+    return crop_planes<GT, GRAY>(C) == 1 ? gy + crop * npx : gy + (crop * C + c0) * npx;
+}
+
 #ifndef STN_BWD_MIN_CTAS
 #define STN_BWD_MIN_CTAS 4
 #endif
@@ -80,7 +97,7 @@ __device__ __forceinline__ void gx_role(const CropParams &p, const CUtensorMap *
                 __syncwarp();
                 touched = true;
             }
-            const GT *gyc = GRAY ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * C + c0) * npx;
+            const GT *gyc = crop_gy<GT, GRAY>(gy, (size_t)(b * p.K + kk), C, c0, npx);
             const Theta th = g.th;
             const int P = g.P, Q = g.Q;
             for (int cp = 0; cp < P; ++cp)
@@ -214,7 +231,7 @@ __device__ __noinline__ void gx_writeout_slow(const CropParams &p, const float *
                 const InvCrop inv = make_inv_crop(th, p.H, p.W, p.oH, p.oW);
                 const GyLoader<GT, GRAY> ld = {(size_t)npx};
                 gather_from_crop<CG>(inv, xs, ys, p.H, p.W, p.oH, p.oW, r0 + row + 1, s0 + col + 1,
-                                     GRAY ? gy + (size_t)(b * p.K + kk) * npx : gy + ((size_t)(b * p.K + kk) * p.C + c0) * npx,
+                                     crop_gy<GT, GRAY>(gy, (size_t)(b * p.K + kk), p.C, c0, npx),
                                      nc, ld, acc);
             }
 #pragma unroll

@@ -173,7 +173,7 @@ __device__ __forceinline__ void theta_role(const CropParams &p, const float *xs,
     const Theta th = load_theta_masked(p.theta + 6 * (size_t)n, p.mask01);
     const int plane = p.H * p.W;
     const float *xb = p.x + (size_t)(n / p.K) * C * plane;
-    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * (GRAY ? 1 : C) * npx;
+    const GT *gyb = reinterpret_cast<const GT *>(p.gy) + (size_t)n * crop_planes<GT, GRAY>(C) * npx;
     float *ggo = p.ggrid_out ? p.ggrid_out + (size_t)n * 2 * npx : nullptr;
     const float *ggu = p.ggrid_up ? p.ggrid_up + (size_t)n * 2 * npx : nullptr;
 

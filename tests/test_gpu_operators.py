@@ -442,7 +442,7 @@ def test_materialised_intermediates_give_the_same_numbers(T):
         with loans_b200.using_config("defer", mode != "eager"):
             tp = rotation_dropout(theta, ratio=0.0)
             if mode == "touch_theta":
-                assert float(tp[:, 0, 1].abs().max()) == 0.0
+                assert float(tp.detach()[:, 0, 1].abs().max()) == 0.0
             points = spatial_transformer_grid(tp, osz)
             if mode == "touch_grid":
                 points.register_hook(lambda g: seen.append(g.detach().clone()))
@@ -541,3 +541,57 @@ def test_same_kernel_on_a_second_device_in_one_process(T):
         T.cuda.synchronize(dev)
         assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max(), dev
         assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max(), dev
+
+
+# ------------------------------------------------------------------------------------------------ round 2: conv-ready crops
+@pytest.mark.parametrize("name,batch,mask,need_gx", [("cfg3", 5, 0.0, True), ("cfg3", 5, 0.0, False), ("cfg2", 64, 0.0, True),
+                                                    ("cfg2", 9, 1.0, True), ("cfg1", 4, 1.0, False), ("cfg5", 12, 0.0, True)])
+def test_channels_last_bf16_crops(T, name, batch, mask, need_gx):
+    """LOANS_STN_FLAG_NHWC4: crops and their gradient as (N, oH, oW, 4) bf16 -- the values of the bf16
+    NCHW crops, permuted, with a zero fourth channel; the backward reads gy in that layout and gives the bits of the NCHW
+    call (same bf16 values in, same kernels).  Oracle: fp32 oracle -> bf16 round-to-nearest-even -> permute."""
+    from tests import gpu_util as G
+    from loans_b200 import _lib
+    from loans_b200.functions import stn_crop
+    wl = W.WORKLOADS[name]
+    d = W.make_inputs(wl, batch=batch, rotate=mask != 0.0)
+    osz = (wl.out_h, wl.out_w)
+    n = batch
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, mask)
+    x = _t(T, d["x"], grad=need_gx)
+    th = _t(T, d["theta"], grad=True)
+    rois, points = stn_crop(x, th, osz, mask01=mask, out_dtype=T.bfloat16, layout="nhwc4")
+    assert tuple(rois.shape) == (n, osz[0], osz[1], 4) and rois.dtype == T.bfloat16
+    got = rois.detach().float().cpu().numpy()
+    assert np.array_equal(got[..., :3], np.transpose(G.bf16_round(y0), (0, 2, 3, 1)))
+    assert np.all(got[..., 3] == 0) and not np.signbit(got[..., 3]).any()
+    assert np.array_equal(points.detach().cpu().numpy(), grid0)
+    # backward: gy arrives channels-last (the padding channel carries garbage on purpose: it must be ignored)
+    gy_r = G.bf16_round(d["gy"])
+    gy_cl = np.concatenate([np.transpose(gy_r, (0, 2, 3, 1)), np.full((n,) + osz + (1,), 123.0, np.float32)], axis=3)
+    rois.backward(_t(T, gy_cl).to(T.bfloat16))
+    k_nhwc = _lib.last_kernel()
+    x2 = _t(T, d["x"], grad=need_gx)
+    th2 = _t(T, d["theta"], grad=True)
+    rois2, _ = stn_crop(x2, th2, osz, mask01=mask, out_dtype=T.bfloat16)
+    rois2.backward(_t(T, gy_r).to(T.bfloat16))
+    assert _lib.last_kernel() == k_nhwc                      # same dispatch as the planar call
+    assert T.equal(th.grad, th2.grad)
+    if need_gx:
+        assert T.equal(x.grad, x2.grad)
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, gy_r, None, mask)
+    assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max()
+    if need_gx:
+        assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * np.abs(gx0).max()
+
+
+def test_channels_last_needs_three_channel_bf16(T):
+    from loans_b200.functions import InvalidType, stn_crop
+    x = T.zeros(2, 3, 8, 8, device="cuda")
+    th = T.zeros(2, 2, 3, device="cuda")
+    with pytest.raises(InvalidType):
+        stn_crop(x, th, (4, 4), layout="nhwc4")                                    # float32 crops
+    with pytest.raises(InvalidType):
+        stn_crop(T.zeros(2, 1, 8, 8, device="cuda"), th, (4, 4), out_dtype=T.bfloat16, layout="nhwc4")
+    with pytest.raises(InvalidType):
+        stn_crop(x, th, (4, 4), out_dtype=T.bfloat16, layout="nhwc4", grayscale=True)
