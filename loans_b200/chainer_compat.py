@@ -3,24 +3,39 @@
     import loans_b200.chainer_compat as stn
     stn.install()            # once, before sheep/sheep_localizer.py is imported
 
-rebinds ``chainer.functions.spatial_transformer_grid`` / ``spatial_transformer_sampler`` to the FunctionNodes
-below and registers a ``functions.rotation_droput`` module exposing ``rotation_dropout`` / ``RotationDropout``,
-so that reference ``sheep/sheep_localizer.py``, ``sheep/sheep_updater.py`` and ``iou/iou_regressor.py`` run unchanged
-(they reach the three operators only through those names: sheep_localizer.py:2,12,61-63,169-171).
+rebinds ``chainer.functions.spatial_transformer_grid`` / ``spatial_transformer_sampler`` to the functions below and
+registers a ``functions.rotation_droput`` module exposing ``rotation_dropout`` / ``RotationDropout``, so that reference
+``sheep/sheep_localizer.py``, ``sheep/sheep_updater.py`` and ``iou/iou_regressor.py`` run unchanged (they reach the three
+operators only through those names: sheep_localizer.py:2,12,61-63,169-171).
 
-Chainer and cupy are NOT installed in the build container or on the GPU box (chainer==4.1.0 / cupy==4.1.0,
-reference requirements.txt:1-3, are not installable offline), so this module is import-guarded and has only
-been exercised as far as ``tests/test_abi_and_host.py::test_chainer_binding_is_import_guarded`` goes; the same
-C-ABI calls are what the torch front end (loans_b200/functions) makes and what the GPU parity tests check.
-Everything here is pointer plumbing: ``cupy.ndarray.data.ptr`` in, ``cupy.cuda.get_current_stream().ptr`` as the
-stream, outputs allocated from cupy's pool.
+How the three calls reach the fused kernels (``install(fuse=...)``):
+
+``"full"`` (default)  ``rotation_dropout`` runs its 6-floats-per-crop kernel and notes (theta_in, mask value) on its output;
+    ``spatial_transformer_grid`` allocates ``points`` WITHOUT launching and passes the note on; ``spatial_transformer_sampler``
+    launches ``loans_stn_crop_fwd(theta_in, mask01=<the draw>)`` once -- it writes the crops and fills ``points`` -- and its
+    backward is one ``loans_stn_crop_bwd`` with the same mask (the band / table kernels at LoANs' ratio 0.0), gradient
+    straight to the un-masked theta.  A gradient arriving on ``points`` (corner regularisers) takes the grid node's own
+    tiny backward.  Contract: ``points`` holds its values only after the sampler call that follows -- exactly the
+    reference's call order; use another mode for code that reads the grid in between.
+``"sampler"``  grid computed eagerly by the grid node; the sampler, handed that very array, still samples from theta in
+    registers (the masked theta, ``LOANS_STN_FLAG_UPRIGHT`` when the dropout zeroed the rotation terms).  Assumes nobody
+    edits the grid array in place between the two calls (cupy arrays carry no version counter).
+``"off"``  three independent nodes (explicit-grid sampler): no assumption at all.
+
+Chainer and cupy are NOT installed in the build container or on the GPU box (chainer==4.1.0 / cupy==4.1.0, reference
+requirements.txt:1-3, are not installable offline).  The module is import-guarded; it is EXECUTED by
+``tests/test_gpu_chainer_binding.py`` against a stand-in for the two packages (tests/chainer_standin: Variable, the v4
+FunctionNode protocol, type_check, a cupy ndarray over torch memory), which proves the code paths and the numbers, not
+compatibility with a real Chainer build -- treat it as experimental until it has run against chainer 4.x.
+Everything here is pointer plumbing: ``cupy.ndarray.data.ptr`` in, ``cupy.cuda.get_current_stream().ptr`` as the stream,
+outputs allocated from cupy's pool.
 """
 import sys
 import types
 
 from loans_b200 import _lib
 
-try:                                                     # pragma: no cover - chainer is absent in this environment
+try:
     import chainer
     from chainer import cuda, function_node
     from chainer.utils import type_check
@@ -28,6 +43,8 @@ try:                                                     # pragma: no cover - ch
 except ImportError:
     chainer = None
     HAVE_CHAINER = False
+
+_STATE = {"fuse": "full"}
 
 
 def _require():
@@ -50,7 +67,7 @@ def _gpu_only(*arrays):
             raise RuntimeError("loans_b200 runs on cupy arrays only (no CPU fallback): move the model with to_gpu()")
 
 
-if HAVE_CHAINER:                                         # pragma: no cover
+if HAVE_CHAINER:
 
     class RotationDropout(function_node.FunctionNode):
         """reference functions/rotation_droput.py:9-48 (old-style Function there; same semantics)."""
@@ -75,6 +92,7 @@ if HAVE_CHAINER:                                         # pragma: no cover
                 if not hasattr(self, 'mask_value') or self.mask_value is None:
                     self.mask_value = float(bool(xp.random.rand(1) < self.dropout_ratio))     # :41, one draw per call
                 value = self.mask_value
+            self.value = value
             y = xp.empty_like(x)
             _lib.check(_lib.lib().loans_stn_rotation_dropout(_ptr(x), value, _ptr(y), x.shape[0], _stream()),
                        "loans_stn_rotation_dropout")
@@ -90,11 +108,20 @@ if HAVE_CHAINER:                                         # pragma: no cover
             return chainer.Variable(gx),
 
     def rotation_dropout(x, ratio=.5, **kwargs):
-        return RotationDropout(ratio).apply((x,))[0]
+        node = RotationDropout(ratio)
+        y, = node.apply((x,))
+        x_var = node.inputs[0]
+        x_arr = x_var.data
+        if isinstance(x_arr, cuda.ndarray) and x_arr.dtype == cuda.cupy.float32:
+            # note for the grid node: where this theta came from (checked again by pointer before it is trusted)
+            y._stn_dropout = {"theta_in": x_var, "theta_in_ptr": _ptr(x_arr), "mask01": node.value,
+                              "can_backprop": node.mask_value is not None, "array": y.data, "ptr": _ptr(y.data)}
+        return y
 
     class SpatialTransformerGrid(function_node.FunctionNode):
-        def __init__(self, output_shape):
+        def __init__(self, output_shape, defer=False):
             self.output_shape = tuple(int(v) for v in output_shape)
+            self.defer = defer
 
         def check_type_forward(self, in_types):
             type_check.expect(in_types.size() == 1)
@@ -109,8 +136,9 @@ if HAVE_CHAINER:                                         # pragma: no cover
             theta = xp.ascontiguousarray(theta)
             oh, ow = self.output_shape
             grid = xp.empty((theta.shape[0], 2, oh, ow), dtype=xp.float32)
-            _lib.check(_lib.lib().loans_stn_grid_fwd(_ptr(theta), _ptr(grid), theta.shape[0], oh, ow, _stream()),
-                       "loans_stn_grid_fwd")
+            if not self.defer:            # "full" mode: the sampler's fused kernel fills it
+                _lib.check(_lib.lib().loans_stn_grid_fwd(_ptr(theta), _ptr(grid), theta.shape[0], oh, ow, _stream()),
+                           "loans_stn_grid_fwd")
             return grid,
 
         def backward(self, indexes, grad_outputs):
@@ -122,11 +150,23 @@ if HAVE_CHAINER:                                         # pragma: no cover
             return chainer.Variable(gtheta),
 
     class FusedSampler(function_node.FunctionNode):
-        """sampler whose grid came straight from our grid node: inputs (x, theta); coordinates are recomputed
-        from theta in registers (loans_stn_crop_fwd / _bwd), the gradient goes to theta directly."""
+        """sampler whose grid came straight from our grid node: inputs (x, theta); coordinates are recomputed from theta in
+        registers (loans_stn_crop_fwd / _bwd), the gradient goes to theta directly.  ``mask01``: the rotation-dropout value
+        folded into the kernel (theta is then the UN-masked theta); ``grid_out``: the grid node's deferred output, filled by
+        the same launch; ``upright``: theta is already masked to axis-aligned boxes (LOANS_STN_FLAG_UPRIGHT)."""
 
-        def __init__(self, output_shape):
-            self.output_shape = output_shape
+        def __init__(self, output_shape, mask01=1.0, grid_out=None, upright=False, can_backprop=True):
+            self.output_shape = tuple(int(v) for v in output_shape)
+            self.mask01 = float(mask01)
+            self.grid_out = grid_out
+            self.upright = bool(upright)
+            self.can_backprop = bool(can_backprop)
+
+        def check_type_forward(self, in_types):
+            type_check.expect(in_types.size() == 2)
+            x_type, theta_type = in_types
+            type_check.expect(x_type.dtype.char == 'f', theta_type.dtype.char == 'f', x_type.ndim == 4, theta_type.ndim == 3,
+                              theta_type.shape[1] == 2, theta_type.shape[2] == 3, x_type.shape[0] == theta_type.shape[0])
 
         def forward(self, inputs):
             x, theta = inputs
@@ -137,21 +177,28 @@ if HAVE_CHAINER:                                         # pragma: no cover
             b, c, h, w = x.shape
             oh, ow = self.output_shape
             y = xp.empty((b, c, oh, ow), dtype=xp.float32)
-            _lib.check(_lib.lib().loans_stn_crop_fwd(_ptr(x), _ptr(theta), 1.0, _ptr(y), None, b, 1, c, h, w, oh, ow,
-                                                     _lib.F32, _stream()), "loans_stn_crop_fwd")
+            with cuda.get_device_from_array(x):
+                _lib.check(_lib.lib().loans_stn_crop_fwd(_ptr(x), _ptr(theta), self.mask01, _ptr(y), _ptr(self.grid_out),
+                                                         b, 1, c, h, w, oh, ow, _lib.F32, _stream()), "loans_stn_crop_fwd")
+            self.grid_out = None
             return y,
 
         def backward(self, indexes, grad_outputs):
+            if not self.can_backprop:
+                raise AttributeError("'RotationDropout' object has no attribute 'mask'")    # as the reference, :47-48
             xp = cuda.cupy
-            x, theta = (v.data for v in self.get_retained_inputs())
+            x, theta = (xp.ascontiguousarray(v.data) for v in self.get_retained_inputs())
             gy = xp.ascontiguousarray(grad_outputs[0].data)
             b, c, h, w = x.shape
             oh, ow = self.output_shape
             need_gx = 0 in indexes                      # LoANs passes the frames as a raw array: never needed there
             gx = xp.empty_like(x) if need_gx else None
             gtheta = xp.empty_like(theta)
-            _lib.check(_lib.lib().loans_stn_crop_bwd(_ptr(x), _ptr(theta), 1.0, _ptr(gy), None, _ptr(gtheta), _ptr(gx), None,
-                                                     b, 1, c, h, w, oh, ow, _lib.F32, _stream()), "loans_stn_crop_bwd")
+            flags = _lib.FLAG_UPRIGHT if self.upright else 0
+            with cuda.get_device_from_array(x):
+                _lib.check(_lib.lib().loans_stn_crop_bwd_ex(_ptr(x), _ptr(theta), self.mask01, _ptr(gy), None, None, _ptr(gtheta),
+                                                            _ptr(gx), None, flags, b, 1, c, h, w, oh, ow, _lib.F32, _stream()),
+                           "loans_stn_crop_bwd_ex")
             return (chainer.Variable(gx) if need_gx else None), chainer.Variable(gtheta)
 
     class SpatialTransformerSampler(function_node.FunctionNode):
@@ -198,19 +245,38 @@ if HAVE_CHAINER:                                         # pragma: no cover
     def spatial_transformer_grid(theta, output_shape, **kwargs):
         _no_kwargs(kwargs)
         theta = theta if isinstance(theta, chainer.Variable) else chainer.Variable(theta)
-        grid, = SpatialTransformerGrid(output_shape).apply((theta,))
-        grid._stn_origin = (theta, id(grid.data))               # note for the sampler: which theta this grid came from
+        fuse = _STATE["fuse"]
+        drop = getattr(theta, '_stn_dropout', None)
+        if drop is not None and not (theta.data is drop["array"] and _ptr(theta.data) == drop["ptr"]
+                                     and _ptr(drop["theta_in"].data) == drop["theta_in_ptr"]):
+            drop = None                                              # not (or no longer) the array our dropout node returned
+        ok = isinstance(theta.data, cuda.ndarray) and theta.data.dtype == cuda.cupy.float32
+        defer = fuse == "full" and ok
+        grid, = SpatialTransformerGrid(output_shape, defer=defer).apply((theta,))
+        if fuse != "off" and ok:
+            # note for the sampler: which theta this grid is the image of
+            grid._stn_origin = {"array": grid.data, "ptr": _ptr(grid.data), "pending": defer,
+                                "theta": theta, "theta_ptr": _ptr(theta.data), "dropout": drop}
         return grid
 
     def spatial_transformer_sampler(x, grid, **kwargs):
         _no_kwargs(kwargs)
         origin = getattr(grid, '_stn_origin', None)
-        if origin is not None and origin[1] == id(grid.data) and origin[0].shape[0] == grid.shape[0]:
-            return FusedSampler(grid.shape[2:]).apply((x, origin[0]))[0]
+        if origin is not None and grid.data is origin["array"] and _ptr(grid.data) == origin["ptr"] and \
+                _ptr(origin["theta"].data) == origin["theta_ptr"]:
+            drop, shape = origin["dropout"], grid.shape[2:]
+            if origin["pending"]:
+                origin["pending"] = False                            # the launch below fills the grid array
+                if drop is not None:                                 # un-masked theta + the draw: one kernel, mask folded in
+                    node = FusedSampler(shape, mask01=drop["mask01"], grid_out=grid.data, can_backprop=drop["can_backprop"])
+                    return node.apply((x, drop["theta_in"]))[0]
+                return FusedSampler(shape, grid_out=grid.data).apply((x, origin["theta"]))[0]
+            upright = drop is not None and drop["mask01"] == 0.0
+            return FusedSampler(shape, upright=upright).apply((x, origin["theta"]))[0]
         return SpatialTransformerSampler().apply((x, grid))[0]
 
 
-if HAVE_CHAINER:                                         # pragma: no cover
+if HAVE_CHAINER:
 
     def prepare_images(self, images):
         """Drop-in for SheepLocalizer.prepare_images / Resnet50SheepLocalizer.prepare_images (reference
@@ -233,11 +299,15 @@ if HAVE_CHAINER:                                         # pragma: no cover
             cls.prepare_images = prepare_images
 
 
-def install():
-    """Rebind the three operator names the reference uses.  Call before importing sheep.sheep_localizer."""
+def install(fuse="full"):
+    """Rebind the three operator names the reference uses.  Call before importing sheep.sheep_localizer.
+    ``fuse``: "full" (default) / "sampler" / "off", see the module docstring."""
     _require()
-    import chainer.functions as F                              # pragma: no cover
-    F.spatial_transformer_grid = spatial_transformer_grid      # pragma: no cover
+    if fuse not in ("full", "sampler", "off"):
+        raise ValueError("fuse must be 'full', 'sampler' or 'off'")
+    _STATE["fuse"] = fuse
+    import chainer.functions as F
+    F.spatial_transformer_grid = spatial_transformer_grid
     F.spatial_transformer_sampler = spatial_transformer_sampler
     F.array.spatial_transformer_grid.spatial_transformer_grid = spatial_transformer_grid
     F.array.spatial_transformer_sampler.spatial_transformer_sampler = spatial_transformer_sampler

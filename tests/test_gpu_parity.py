@@ -435,3 +435,34 @@ def test_reference_gpu_kernels_agree_with_oracle_and_cuda_path(G, name, batch, m
         ref = ref.cpu().numpy()
         assert G.rel_max(orc, ref) <= GRAD_TOL, (what, "oracle vs cuDNN", G.rel_max(orc, ref))
         assert G.rel_max(ours, ref) <= GRAD_TOL, (what, "CUDA path vs cuDNN", G.rel_max(ours, ref))
+
+
+# ------------------------------------------------------------------------------------------------ the benched dispatch, full size
+@pytest.mark.parametrize("name,need_gx,kernel", [("cfg2", True, "stn_bwd_band_kernel/row"), ("cfg2", False, "stn_bwd_theta_tab_kernel"),
+                                                 ("cfg5", True, "stn_bwd_band_kernel/row"), ("cfg5", False, "stn_bwd_theta_tab_kernel"),
+                                                 ("cfg3", True, "stn_bwd_band_kernel/cta")])
+def test_benched_dispatch_at_full_size_against_the_oracle(G, name, need_gx, kernel):
+    """bench.py's headline (cfg2, batch 64) and its `configs` block (cfg5 batch 1024 -- two CTAs per crop --, cfg3) with the
+    AUTOMATIC dispatch rule, as LoANs ships the path (mask 0): which kernel ran is asserted, and EVERY frame is compared with
+    the C oracle (cfg3: the first 48 of its 256 frames go through the same launch geometry rule, crops x CTAs >= 200 x passes)."""
+    from loans_b200 import _lib
+    wl = W.WORKLOADS[name]
+    batch = 48 if name == "cfg3" else wl.batch
+    d = W.make_inputs(wl, batch=batch, rotate=False, with_ggrid=True)
+    osz = (wl.out_h, wl.out_w)
+    bf16 = wl.out_dtype == "bf16"
+    gy = G.bf16_round(d["gy"]) if bf16 else d["gy"]
+    y, grid = G.crop_fwd(d["x"], d["theta"], osz, 0.0, 1, bf16=bf16)
+    assert _lib.last_kernel() == "stn_fwd_kernel"
+    gt, gx, ggo = G.crop_bwd(d["x"], d["theta"], osz, gy, d["ggrid"], 0.0, 1, bf16=bf16, need_gx=need_gx)
+    assert _lib.last_kernel() == kernel
+    y0, grid0 = oc.crop_forward(d["x"], d["theta"], osz, 0.0)
+    gt0, gx0, gg0 = oc.crop_backward(d["x"], d["theta"], osz, gy, d["ggrid"], 0.0)
+    assert np.array_equal(grid, grid0)
+    assert np.array_equal(y, G.bf16_round(y0) if bf16 else y0)
+    assert np.array_equal(ggo, gg0)
+    sc = np.abs(gt0).reshape(batch, -1).max(axis=1)[:, None, None]
+    assert (np.abs(gt - gt0) <= GRAD_TOL * sc).all()                       # per crop, against that crop's own largest entry
+    if need_gx:
+        per_frame = np.abs(gx - gx0).reshape(batch, -1).max(axis=1) / np.abs(gx0).reshape(batch, -1).max(axis=1)
+        assert per_frame.max() <= 2e-6, per_frame.max()
