@@ -767,6 +767,25 @@ def run_ours(args):
             next_rows["prepare_images"] = {"us": ms_p * 1e3, "frames_per_s": world * B / (ms_p * 1e-3),
                                            "algorithmic_bytes": nb, "achieved_gbs": nb / (ms_p * 1e-3) / 1e9,
                                            "what": "SheepLocalizer.prepare_images as one kernel (uint8 quantise, RGB->BGR, mean), x*255 folded in"}
+        if C == 3:
+            # the loader's frame path (8f rank 4): decoded uint8 frames as `-r 512` extracts them (384 x 512) -> LANCZOS resize to
+            # this workload's frame size -> float32 NCHW / 255, written into the rotating frame buffers
+            from loans_b200.functions import FrameIngest
+            fh, fw = (384, 512) if (H, Wd) != (384, 512) else (512, 512)
+            raw = [torch.randint(0, 256, (B, fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(min(S, 4))]
+            ing = FrameIngest(B, (fh, fw), (H, Wd), device=dev)
+            tgt = [e["gx"] if need_gx else prep_out for e in sets]
+            ing(raw[0], out=tgt[0])
+            g_ing = hz.capture(lambda: [ing(raw[i % len(raw)], out=tgt[i]) for i in range(S)])
+            for _ in range(3):
+                g_ing.replay()
+            ms_i = pb.per_launch(g_ing, steps)
+            nb = B * fh * fw * 3 + 4 * B * C * H * Wd
+            next_rows["frame_ingest"] = {"us": ms_i * 1e3, "frames_per_s": world * B / (ms_i * 1e-3), "algorithmic_bytes": nb,
+                                         "achieved_gbs": nb / (ms_i * 1e-3) / 1e9, "from": [fh, fw], "to": [H, Wd],
+                                         "what": "resize_image(frame, image_size) / 255 of the reference's datasets (PIL LANCZOS, bit-exact) "
+                                                 "for the batch on the device: uint8 HWC -> float32 NCHW, two integer kernels"}
+            del raw, g_ing
         cor = torch.empty((N, 2, 2, 2), dtype=torch.float32, device=dev)
         gcor = torch.randn((N, 2, 2, 2), dtype=torch.float32, device=dev)
 

@@ -83,6 +83,19 @@ int loans_stn_rotation_dropout(const float *theta_in, float mask01, float *theta
  *      reference takes no gradient through it (it builds new arrays on the host). */
 int loans_stn_prepare_images(const float *x, float scale, float *out, int b, int c, int h, int w, void *stream);
 
+/* ---- f4  the loader's frame path (reference common/datasets/image_dataset.py:16-28 resize_image, :98 and :181 `image / 255`):
+ *          Image.fromarray(uint8 HWC).convert('RGB').resize((ow, oh), Image.LANCZOS) -> float32 CHW -> / 255
+ *      for a batch of decoded frames on the device.  frames_hwc (b,h,w,3) uint8 -> out_nchw (b,3,oh,ow) f32 in [0,1], bit for
+ *      bit what Pillow's 8-bit Lanczos resampling gives (two fixed-point passes, coefficient tables computed on the host in
+ *      float64 exactly as Pillow does).  h == oh and w == ow: the conversion alone.
+ *      workspace: caller-owned device memory of loans_stn_ingest_workspace_bytes(b,h,w,oh,ow) bytes (coefficient tables +
+ *      the intermediate image); loans_stn_ingest_prepare fills the tables for (h,w,oh,ow) once (a host-to-device copy ordered
+ *      on `stream`: not capturable into a CUDA graph); loans_stn_ingest_u8 then only launches kernels, any number of times. */
+long long loans_stn_ingest_workspace_bytes(int b, int h, int w, int oh, int ow);
+int loans_stn_ingest_prepare(void *workspace, int h, int w, int oh, int ow, void *stream);
+int loans_stn_ingest_u8(const unsigned char *frames_hwc, float *out_nchw, const void *workspace,
+                        int b, int h, int w, int oh, int ow, void *stream);
+
 /* ---- a2  F.spatial_transformer_grid forward / backward (call site sheep/sheep_localizer.py:62,170;
  *      arithmetic in chainer 4.1.0 chainer/functions/array/spatial_transformer_grid.py, restated in
  *      oracle/stn_numpy.py:grid_forward/grid_backward). */

@@ -35,6 +35,9 @@ SIGNATURES = {
     "loans_stn_configure": [_i, _i],
     "loans_stn_rotation_dropout": [_vp, _fl, _vp, _i, _vp],
     "loans_stn_prepare_images": [_vp, _fl, _vp, _i, _i, _i, _i, _vp],
+    "loans_stn_ingest_workspace_bytes": [_i, _i, _i, _i, _i],
+    "loans_stn_ingest_prepare": [_vp, _i, _i, _i, _i, _vp],
+    "loans_stn_ingest_u8": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "loans_stn_grid_fwd": [_vp, _vp, _i, _i, _i, _vp],
     "loans_stn_grid_bwd": [_vp, _vp, _i, _i, _i, _vp],
     "loans_stn_sampler_fwd": [_vp, _vp, _vp] + [_i] * 8 + [_vp],
@@ -73,6 +76,7 @@ def lib():
         handle.loans_stn_last_error.restype = ctypes.c_char_p
         handle.loans_stn_launch_count.restype = ctypes.c_ulonglong
         handle.loans_stn_last_kernel.restype = ctypes.c_char_p
+        handle.loans_stn_ingest_workspace_bytes.restype = ctypes.c_longlong
         if handle.loans_stn_abi_version() != ABI_VERSION:
             raise StnLibraryError("libloans_stn.so ABI %d != expected %d" % (handle.loans_stn_abi_version(), ABI_VERSION))
         _lib = handle

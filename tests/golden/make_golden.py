@@ -21,6 +21,11 @@
    values on the quantisation boundaries.  Chainer is absent, so the statement sequence and the mean constants are
    restated from the published source (parity unpinned for them); PIL's part is executed, not restated.
 
+4. ``ingest_lanczos.npz`` -- the loader's frame path (reference common/datasets/image_dataset.py:16-28, :98): the reference's
+   own statement sequence (``Image.fromarray(...).convert('RGB').resize(..., Image.LANCZOS)``, float32 CHW, ``/ 255``) EXECUTED
+   with the real PIL on seeded uint8 frames -- down-sampling, up-sampling, one axis only, no resampling.  Pins
+   oracle/ingest_numpy.py and the CUDA kernels (bit for bit).
+
 /root/reference is read at generation time only; nothing under tests/ reads it at test time.
 """
 import importlib.util
@@ -186,7 +191,32 @@ def make_prepare_images():
     print("prepare_images.npz:", len(shapes), "cases (literal resnet.prepare statement sequence through PIL)")
 
 
+def make_ingest():
+    from oracle import ingest_numpy as ig
+    rng = np.random.default_rng(20181018)
+    cases = {}
+    shapes = [(37, 53, 20, 31), (16, 16, 40, 24), (24, 20, 24, 20), (90, 120, 75, 75), (24, 32, 56, 56), (51, 77, 51, 30),
+              (9, 200, 3, 7), (300, 5, 10, 5), (64, 48, 32, 48)]
+    for i, (h, w, oh, ow) in enumerate(shapes):
+        f = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        f[0, ::3, ::5] = 255                                    # saturated / black pixels next to noise: clipping of the ringing
+        f[0, 1::4, 2::7] = 0
+        out = ig.pil_reference(f, (oh, ow))                      # the real PIL
+        assert np.array_equal(out, ig.ingest(f, (oh, ow))), "oracle restatement differs from PIL at %s" % ((h, w, oh, ow),)
+        out_u8 = np.rint(out * 255).astype(np.uint8)            # stored as the uint8 image PIL returned (float32 / 255 is
+        assert np.array_equal(out_u8.astype(np.float32) / 255, out)   # re-applied by the tests: the reference's last statement)
+        cases["c%02d_frames" % i] = f
+        cases["c%02d_out_u8" % i] = out_u8
+        cases["c%02d_size" % i] = np.array([oh, ow])
+    cases["n_cases"] = np.array(len(shapes))
+    import PIL
+    cases["pil_version"] = np.array(PIL.__version__)
+    np.savez_compressed(os.path.join(HERE, "ingest_lanczos.npz"), **cases)
+    print("ingest_lanczos.npz: %d cases from PIL %s" % (len(shapes), PIL.__version__))
+
+
 if __name__ == "__main__":
     make_rotation_dropout()
     make_stn_small()
     make_prepare_images()
+    make_ingest()

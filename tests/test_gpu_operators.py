@@ -595,3 +595,39 @@ def test_channels_last_needs_three_channel_bf16(T):
         stn_crop(T.zeros(2, 1, 8, 8, device="cuda"), th, (4, 4), out_dtype=T.bfloat16, layout="nhwc4")
     with pytest.raises(InvalidType):
         stn_crop(x, th, (4, 4), out_dtype=T.bfloat16, layout="nhwc4", grayscale=True)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: loader frame path
+def test_frame_ingest_matches_pil_fixtures_and_oracle(T):
+    """uint8 HWC frames -> float32 NCHW in [0,1] with the loader's LANCZOS resize (reference
+    common/datasets/image_dataset.py:16-28,98) on the device, bit for bit what the real PIL produced (fixtures) and what
+    the oracle restatement gives at BASELINE's frame sizes."""
+    from loans_b200 import _lib
+    from loans_b200.functions import FrameIngest, ingest_frames
+    from oracle import ingest_numpy as ig
+    g = np.load(os.path.join(GOLDEN, "ingest_lanczos.npz"))
+    for i in range(int(g["n_cases"])):
+        p = "c%02d_" % i
+        out = ingest_frames(T.from_numpy(g[p + "frames"]).cuda(), tuple(int(v) for v in g[p + "size"]))
+        assert np.array_equal(out.cpu().numpy(), g[p + "out_u8"].astype(np.float32) / 255), i
+    rng = np.random.default_rng(3)
+    for (b, h, w, size) in [(3, 384, 512, (224, 224)), (2, 512, 512, (224, 224)), (2, 224, 224, None), (2, 200, 300, (512, 512)),
+                            (1, 1, 1, (4, 4)), (2, 75, 75, (75, 224))]:
+        f = rng.integers(0, 256, (b, h, w, 3), dtype=np.uint8)
+        n0 = _lib.launch_count()
+        op = FrameIngest(b, (h, w), size)
+        out = op(T.from_numpy(f).cuda())
+        assert np.array_equal(out.cpu().numpy(), ig.ingest(f, size)), (b, h, w, size)
+        both = size is not None and size[0] != h and size[1] != w
+        assert _lib.launch_count() - n0 == (2 if both else 1)
+        # a prepared ingest is graph-capturable: kernels only
+        fd = T.from_numpy(f).cuda()
+        od = T.empty_like(out)
+        gr = T.cuda.CUDAGraph()
+        with T.cuda.graph(gr):
+            op(fd, out=od)
+        gr.replay()
+        T.cuda.synchronize()
+        assert T.equal(od, out)
+    with pytest.raises(Exception):
+        ingest_frames(T.zeros(2, 8, 8, 3, device="cuda"), (4, 4))            # float frames are refused
