@@ -76,81 +76,130 @@ __device__ __forceinline__ int clip8(int acc)
 }
 
 // horizontal pass: rows x w x 3 bytes -> rows x ow x 3 bytes (or, TO_FLOAT, straight to the float32 NCHW output when the
-// height does not change)
+// height does not change).  A CTA stages kIngestRows source rows in shared memory with coalesced 16-byte loads (the taps of
+// neighbouring output pixels overlap: every source byte is read from DRAM once) and its threads walk the rows' output pixels.
+constexpr int kIngestRows = 8;
+
 template <bool TO_FLOAT>
 __global__ void __launch_bounds__(kThreads) ingest_h_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ tmp,
                                                             float *__restrict__ out, const int *__restrict__ tab, int ksize,
-                                                            long long npix, int h, int w, int ow)
+                                                            long long rows, int h, int w, int ow)
 {
+    extern __shared__ __align__(16) unsigned char srow[];             // kIngestRows x pitch source bytes | kIngestRows x ow * 3 output bytes
     pdl_launch_dependents();
     pdl_wait();
-    const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= npix) return;
-    const long long row = idx / ow;
-    const int xx = (int)(idx - row * ow);
-    const int *rec = tab + (size_t)xx * (2 + ksize);
-    const int xmin = rec[0], n = rec[1];
-    const unsigned char *p = src + (row * w + xmin) * 3;
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    for (int x = 0; x < n; ++x) {
-        const int k = rec[2 + x];
-        s0 += (int)p[3 * x] * k;
-        s1 += (int)p[3 * x + 1] * k;
-        s2 += (int)p[3 * x + 2] * k;
+    const long long r0 = (long long)blockIdx.x * kIngestRows;
+    const int nr = (int)min((long long)kIngestRows, rows - r0);
+    const int wb = w * 3, pitch = (wb + 15) & ~15;
+    {   // stage: the nr rows are contiguous in the source (HWC, rows back to back)
+        const unsigned char *g = src + r0 * wb;
+        const long long total = (long long)nr * wb;
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (wb & 15) == 0) {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+            uint4 *s4 = reinterpret_cast<uint4 *>(srow);
+            for (int e = threadIdx.x; e < (int)(total >> 4); e += kThreads) s4[e] = __ldg(g4 + e);       // pitch == wb here
+        } else {
+            for (int e = threadIdx.x; e < (int)total; e += kThreads) {
+                const int r = e / wb, c = e - r * wb;
+                srow[r * pitch + c] = __ldg(g + e);
+            }
+        }
     }
-    if (TO_FLOAT) {
-        const long long b = row / h;
-        const int y = (int)(row - b * h);
-        float *o = out + ((size_t)b * 3 * h + y) * ow + xx;
-        const size_t plane = (size_t)h * ow;
-        o[0] = __fdiv_rn((float)clip8(s0), 255.0f);
-        o[plane] = __fdiv_rn((float)clip8(s1), 255.0f);
-        o[2 * plane] = __fdiv_rn((float)clip8(s2), 255.0f);
-    } else {
-        unsigned char *o = tmp + idx * 3;
-        o[0] = (unsigned char)clip8(s0);
-        o[1] = (unsigned char)clip8(s1);
-        o[2] = (unsigned char)clip8(s2);
+    __syncthreads();
+    unsigned char *sout = srow + kIngestRows * pitch;                  // the rows' output bytes, back to back as in tmp
+    for (int it = threadIdx.x; it < nr * ow; it += kThreads) {
+        const int r = it / ow, xx = it - r * ow;
+        const int *rec = tab + (size_t)xx * (2 + ksize);
+        const int xmin = __ldg(rec), n = __ldg(rec + 1);
+        const unsigned char *p = srow + r * pitch + xmin * 3;
+        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+        for (int x = 0; x < n; ++x) {
+            const int k = __ldg(rec + 2 + x);
+            s0 += (int)p[3 * x] * k;
+            s1 += (int)p[3 * x + 1] * k;
+            s2 += (int)p[3 * x + 2] * k;
+        }
+        const long long row = r0 + r;
+        if (TO_FLOAT) {
+            const long long b = row / h;
+            const int y = (int)(row - b * h);
+            float *o = out + ((size_t)b * 3 * h + y) * ow + xx;
+            const size_t plane = (size_t)h * ow;
+            o[0] = __fdiv_rn((float)clip8(s0), 255.0f);
+            o[plane] = __fdiv_rn((float)clip8(s1), 255.0f);
+            o[2 * plane] = __fdiv_rn((float)clip8(s2), 255.0f);
+        } else {
+            unsigned char *o = sout + it * 3;
+            o[0] = (unsigned char)clip8(s0);
+            o[1] = (unsigned char)clip8(s1);
+            o[2] = (unsigned char)clip8(s2);
+        }
+    }
+    if (!TO_FLOAT) {
+        __syncthreads();
+        unsigned char *g = tmp + r0 * ow * 3;
+        const int total = nr * ow * 3;
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && ((kIngestRows * pitch) & 15) == 0) {
+            uint4 *g4 = reinterpret_cast<uint4 *>(g);
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(sout);
+            for (int e = threadIdx.x; e < (total >> 4); e += kThreads) g4[e] = s4[e];
+            for (int e = (total & ~15) + threadIdx.x; e < total; e += kThreads) g[e] = sout[e];
+        } else {
+            for (int e = threadIdx.x; e < total; e += kThreads) g[e] = sout[e];
+        }
     }
 }
 
-// vertical pass + conversion: b x h x ow x 3 bytes -> b x 3 x oh x ow float32 / 255.  ksize == 0: no resampling at all
-// (frames already have the target size): conversion only.
+// vertical pass + conversion: b x h x ow x 3 bytes -> b x 3 x oh x ow float32 / 255.  One CTA per output row: the row's
+// coefficients sit in shared memory, a thread takes four consecutive BYTE columns (pixel x channel, channel fastest, as the
+// source is laid out) with one 32-bit load per tap row, and the finished row goes through shared memory so that each channel
+// plane is written with coalesced float stores.  ksize == 0: no resampling at all (frames already have the target size).
 __global__ void __launch_bounds__(kThreads) ingest_v_kernel(const unsigned char *__restrict__ src, float *__restrict__ out,
-                                                            const int *__restrict__ tab, int ksize, long long npix, int h, int oh, int ow)
+                                                            const int *__restrict__ tab, int ksize, int h, int oh, int ow)
 {
+    extern __shared__ __align__(16) unsigned char vsm[];               // [ksize + 2 ints] [ow * 3 floats]
+    int *rec = reinterpret_cast<int *>(vsm);
+    float *res = reinterpret_cast<float *>(vsm + (((size_t)(ksize + 2) * sizeof(int) + 15) & ~(size_t)15));
     pdl_launch_dependents();
     pdl_wait();
-    const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= npix) return;
-    const long long bo = idx / ow;                      // b * oh + yy
-    const int xx = (int)(idx - bo * ow);
+    const long long bo = blockIdx.x;                    // b * oh + yy
     const long long b = bo / oh;
     const int yy = (int)(bo - b * oh);
-    int v0, v1, v2;
-    if (ksize == 0) {
-        const unsigned char *p = src + ((b * h + yy) * ow + xx) * 3;
-        v0 = p[0]; v1 = p[1]; v2 = p[2];
-    } else {
-        const int *rec = tab + (size_t)yy * (2 + ksize);
-        const int ymin = rec[0], n = rec[1];
-        const unsigned char *p = src + ((b * h + ymin) * ow + xx) * 3;
-        const size_t stride = (size_t)ow * 3;
-        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-        for (int y = 0; y < n; ++y) {
-            const int k = rec[2 + y];
-            s0 += (int)p[0] * k;
-            s1 += (int)p[1] * k;
-            s2 += (int)p[2] * k;
-            p += stride;
-        }
-        v0 = clip8(s0); v1 = clip8(s1); v2 = clip8(s2);
+    const int owb = ow * 3;
+    if (ksize) {
+        for (int e = threadIdx.x; e < ksize + 2; e += kThreads) rec[e] = __ldg(tab + (size_t)yy * (2 + ksize) + e);
+        __syncthreads();
     }
-    float *o = out + ((size_t)b * 3 * oh + yy) * ow + xx;
+    const int ymin = ksize ? rec[0] : yy, n = ksize ? rec[1] : 1;
+    const unsigned char *base = src + (b * h + ymin) * owb;
+    const bool words = (owb & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    for (int q = 4 * threadIdx.x; q < owb; q += 4 * kThreads) {
+        int acc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = ksize ? 1 << (kPrecisionBits - 1) : 0;
+        const unsigned char *p = base + q;
+        const int nb = min(4, owb - q);
+        for (int y = 0; y < n; ++y) {
+            const int k = ksize ? rec[2 + y] : 1;
+            unsigned wv = 0;
+            if (words) wv = __ldg(reinterpret_cast<const unsigned *>(p));
+            else
+                for (int t = 0; t < nb; ++t) wv |= (unsigned)__ldg(p + t) << (8 * t);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t] += (int)((wv >> (8 * t)) & 0xffu) * k;
+            p += owb;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < nb) res[q + t] = __fdiv_rn((float)(ksize ? clip8(acc[t]) : acc[t]), 255.0f);
+    }
+    __syncthreads();
+    float *o = out + ((size_t)b * 3 * oh + yy) * ow;
     const size_t plane = (size_t)oh * ow;
-    o[0] = __fdiv_rn((float)v0, 255.0f);
-    o[plane] = __fdiv_rn((float)v1, 255.0f);
-    o[2 * plane] = __fdiv_rn((float)v2, 255.0f);
+    for (int e = threadIdx.x; e < owb; e += kThreads) {
+        const int ch = e / ow, xx = e - ch * ow;
+        o[ch * plane + xx] = res[xx * 3 + ch];
+    }
 }
 
 struct IngestLayout {
@@ -223,10 +272,11 @@ int loans_stn_ingest_u8(const unsigned char *frames_hwc, float *out_nchw, const 
     const int *tx = reinterpret_cast<const int *>(ws + L.off_x), *ty = reinterpret_cast<const int *>(ws + L.off_y);
     unsigned char *tmp = reinterpret_cast<unsigned char *>(const_cast<char *>(ws + L.off_tmp));
     cudaStream_t s = (cudaStream_t)stream;
-    auto launch = [&](auto kernel, long long npix, auto... args) -> cudaError_t {
+    auto launch = [&](auto kernel, long long ctas, size_t smem, auto... args) -> cudaError_t {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((npix + kThreads - 1) / kThreads));
+        cfg.gridDim = dim3((unsigned)ctas);
         cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
         cudaLaunchAttribute attr[2];
         cfg.attrs = attr;
@@ -236,15 +286,21 @@ int loans_stn_ingest_u8(const unsigned char *frames_hwc, float *out_nchw, const 
     };
     cudaError_t e = cudaSuccess;
     const long long rows = (long long)b * h;
-    if ((rows * (long long)(w > ow ? w : ow) + kThreads) / kThreads > 0x7fffffffLL) return set_error("%s: batch too large", what);
+    const long long h_ctas = (rows + kIngestRows - 1) / kIngestRows;
+    const size_t h_smem = (size_t)kIngestRows * ((((size_t)w * 3 + 15) & ~(size_t)15) + (L.ky ? (size_t)ow * 3 : 0)) + 16;
+    const long long v_ctas = (long long)b * oh;
+    const size_t v_smem = (((size_t)(L.ky + 2) * sizeof(int) + 15) & ~(size_t)15) + sizeof(float) * (size_t)ow * 3;
+    if (h_ctas > 0x7fffffffLL || v_ctas > 0x7fffffffLL) return set_error("%s: batch too large", what);
+    if ((L.kx && h_smem > 48 * 1024) || v_smem > 48 * 1024)
+        return set_error("%s: frame rows of %d -> %d pixels are too wide for the staging buffers", what, w, ow);
     if (L.kx && L.ky) {
-        e = launch(ingest_h_kernel<false>, rows * ow, frames_hwc, tmp, (float *)nullptr, tx, L.kx, rows * ow, h, w, ow);
+        e = launch(ingest_h_kernel<false>, h_ctas, h_smem, frames_hwc, tmp, (float *)nullptr, tx, L.kx, rows, h, w, ow);
         if (e == cudaSuccess)
-            e = launch(ingest_v_kernel, (long long)b * oh * ow, (const unsigned char *)tmp, out_nchw, ty, L.ky, (long long)b * oh * ow, h, oh, ow);
+            e = launch(ingest_v_kernel, v_ctas, v_smem, (const unsigned char *)tmp, out_nchw, ty, L.ky, h, oh, ow);
     } else if (L.kx) {
-        e = launch(ingest_h_kernel<true>, rows * ow, frames_hwc, (unsigned char *)nullptr, out_nchw, tx, L.kx, rows * ow, h, w, ow);
+        e = launch(ingest_h_kernel<true>, h_ctas, h_smem, frames_hwc, (unsigned char *)nullptr, out_nchw, tx, L.kx, rows, h, w, ow);
     } else {
-        e = launch(ingest_v_kernel, (long long)b * oh * ow, frames_hwc, out_nchw, ty, L.ky, (long long)b * oh * ow, h, oh, ow);
+        e = launch(ingest_v_kernel, v_ctas, v_smem, frames_hwc, out_nchw, ty, L.ky, h, oh, ow);
     }
     note_kernel("ingest");
     if (e != cudaSuccess) return set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
