@@ -973,7 +973,38 @@ def run_ours(args):
                "serial": {"value": world * N * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
                           "api": "loans_b200.functions.stn_crop + autograd backward, copy-in / run / copy-out one step at a time"},
                "matches_serial_result": ok}
-        del pipe, outs
+        del pipe
+        # what the LoANs step needs (SURVEY.md 8d "no gx"): decoded uint8 frames up (the `/ 255` conversion on the device),
+        # frames take no gradient, crops + grid + gtheta down -- same pipeline, same kernels minus gx
+        if C == 3 and need_gx and K == 1:
+            hu8 = torch.from_numpy((host0["x"] * 255).astype("uint8").transpose(0, 2, 3, 1).copy()).pin_memory()
+            pipe2 = HostCropPipeline(B, C, H, Wd, (oH, oW), crops_per_frame=K, need_gx=False, out_dtype=ydt, depth=2, device=dev,
+                                     uint8_frames=True)
+            for i in range(4):
+                pipe2.submit(hu8, hth, hgy, outs[i % 2], mask01=mask01)
+            pipe2.drain()
+            n2 = e2e_steps * 4
+            hz.barrier()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(pipe2.s_in)
+            for i in range(n2):
+                pipe2.submit(hu8, hth, hgy, outs[i % 2], mask01=mask01)
+            e1.record(pipe2.s_out)
+            pipe2.drain()
+            torch.cuda.synchronize()
+            hz.sampler.window(t0, time.perf_counter())
+            ms2 = hz.max_over_ranks(e0.elapsed_time(e1))
+            if world > 1:
+                dist.barrier()
+            e2e["loans_step_uint8_frames_no_gx"] = {
+                "value": world * N * n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / n2, "steps": n2,
+                "h2d_bytes_per_step": pipe2.h2d_bytes, "d2h_bytes_per_step": pipe2.d2h_bytes,
+                "what": "the same pipeline as LoANs would drive it: decoded uint8 HWC frames uploaded (a quarter of the bytes; `/ 255` "
+                        "and the NCHW layout by loans_stn_ingest_u8 on the device), frames take no gradient (no gx computed or "
+                        "downloaded), crops + grid + gtheta downloaded.  NOT the headline: the reference arm computes gx"}
+            del pipe2
+        del outs
 
     launches_per_step = pb.launches_per_step
     harness = {"l2": "rotating %d distinct input/output sets (%.0f MB each, %.0f MB total > 126 MB L2)"

@@ -21,7 +21,7 @@ from loans_b200 import _lib
 
 class HostCropPipeline(object):
     def __init__(self, batch, channels, height, width, out_size, crops_per_frame=1, need_gx=True,
-                 out_dtype=torch.float32, depth=2, device=None):
+                 out_dtype=torch.float32, depth=2, device=None, uint8_frames=False):
         if not torch.cuda.is_available():
             raise RuntimeError("HostCropPipeline needs a CUDA device (loans_b200 has no CPU fallback)")
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -33,11 +33,21 @@ class HostCropPipeline(object):
         self.dt_code = _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32
         self.depth = int(depth)
         self.lib = _lib.lib()
+        # uint8_frames: the host hands over DECODED frames, (B,H,W,3) uint8 as the loader reads them, and the `/ 255` float32
+        # NCHW conversion (reference common/datasets/image_dataset.py:98) runs on the device (loans_stn_ingest_u8): a quarter
+        # of the upload
+        self.uint8_frames = bool(uint8_frames)
+        if self.uint8_frames and int(channels) != 3:
+            raise ValueError("uint8 frames are RGB (3 channels)")
         with torch.cuda.device(self.dev):
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
             self.slots = []
+            if self.uint8_frames:
+                from loans_b200.functions.ingest import FrameIngest
+                self.ingest = FrameIngest(b, (h, w), None, device=self.dev)
             for _ in range(self.depth):
                 self.slots.append({
+                    "xu8": torch.empty((b, h, w, 3), dtype=torch.uint8, device=self.dev) if self.uint8_frames else None,
                     "x": torch.empty((b, c, h, w), device=self.dev), "theta": torch.empty((n, 2, 3), device=self.dev),
                     "gy": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
                     "y": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
@@ -45,7 +55,7 @@ class HostCropPipeline(object):
                     "gx": torch.empty((b, c, h, w), device=self.dev) if need_gx else None,
                     "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_out": torch.cuda.Event(), "used": False})
         self.step = 0
-        self.h2d_bytes = 4 * (b * c * h * w + n * 6) + n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4)
+        self.h2d_bytes = (1 if self.uint8_frames else 4) * b * c * h * w + 4 * n * 6 + n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4)
         self.d2h_bytes = n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4) + 4 * (n * 2 * oh * ow + n * 6) \
             + (4 * b * c * h * w if need_gx else 0)
 
@@ -59,7 +69,7 @@ class HostCropPipeline(object):
             with torch.cuda.stream(self.s_in):
                 if s["used"]:
                     self.s_in.wait_event(s["ev_out"])            # the slot's previous results have left the device
-                s["x"].copy_(x_host, non_blocking=True)
+                (s["xu8"] if self.uint8_frames else s["x"]).copy_(x_host, non_blocking=True)
                 s["theta"].copy_(theta_host, non_blocking=True)
                 s["gy"].copy_(gy_host, non_blocking=True)
                 s["ev_in"].record(self.s_in)
@@ -67,6 +77,8 @@ class HostCropPipeline(object):
                 self.s_run.wait_event(s["ev_in"])
                 st = self.s_run.cuda_stream
                 p = lambda t: None if t is None else t.data_ptr()          # noqa: E731
+                if self.uint8_frames:
+                    self.ingest(s["xu8"], out=s["x"])
                 _lib.check(self.lib.loans_stn_crop_fwd(p(s["x"]), p(s["theta"]), float(mask01), p(s["y"]), p(s["grid"]),
                                                        n, k, c, h, w, oh, ow, self.dt_code, st), "loans_stn_crop_fwd")
                 _lib.check(self.lib.loans_stn_crop_bwd(p(s["x"]), p(s["theta"]), float(mask01), p(s["gy"]), None, p(s["gtheta"]),
@@ -87,3 +99,17 @@ class HostCropPipeline(object):
         self.s_out.synchronize()
         self.s_run.synchronize()
         self.s_in.synchronize()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.drain()
+
+    def __del__(self):
+        # the slot tensors are used on the side streams only: nothing may hand them back to the allocator while copies or
+        # kernels are still in flight
+        try:
+            self.drain()
+        except Exception:
+            pass

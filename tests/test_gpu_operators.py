@@ -631,3 +631,27 @@ def test_frame_ingest_matches_pil_fixtures_and_oracle(T):
         assert T.equal(od, out)
     with pytest.raises(Exception):
         ingest_frames(T.zeros(2, 8, 8, 3, device="cuda"), (4, 4))            # float frames are refused
+
+
+def test_host_buffer_pipeline_with_decoded_uint8_frames(T):
+    """HostCropPipeline(uint8_frames=True): the host uploads decoded (B,H,W,3) uint8 frames, `/ 255` and the NCHW layout happen
+    on the device; frames take no gradient (what the LoANs step needs).  Same numbers as the oracle on x = u8 / 255."""
+    from loans_b200.pipeline import HostCropPipeline
+    wl = W.WORKLOADS["cfg1"]
+    osz = (wl.out_h, wl.out_w)
+    rng = np.random.default_rng(9)
+    with HostCropPipeline(3, 3, wl.height, wl.width, osz, need_gx=False, depth=2, uint8_frames=True) as pipe:
+        cases = []
+        for i in range(3):
+            d = W.make_inputs(wl, seed=200 + i, batch=3)
+            u8 = rng.integers(0, 256, (3, wl.height, wl.width, 3), dtype=np.uint8)
+            h = {"x": T.from_numpy(u8).pin_memory(), "theta": T.from_numpy(d["theta"]).pin_memory(), "gy": T.from_numpy(d["gy"]).pin_memory()}
+            o = {"y": T.empty((3, 3) + osz).pin_memory(), "grid": T.empty((3, 2) + osz).pin_memory(), "gtheta": T.empty((3, 2, 3)).pin_memory()}
+            cases.append((u8, d, h, o))
+            pipe.submit(h["x"], h["theta"], h["gy"], o, mask01=0.0)
+    for u8, d, h, o in cases:
+        x = u8.transpose(0, 3, 1, 2).astype(np.float32) / np.float32(255)          # reference image_dataset.py:98
+        y0, g0 = oc.crop_forward(x, d["theta"], osz, 0.0)
+        gt0, _, _ = oc.crop_backward(x, d["theta"], osz, d["gy"], None, 0.0)
+        assert np.array_equal(o["y"].numpy(), y0) and np.array_equal(o["grid"].numpy(), g0)
+        assert np.abs(o["gtheta"].numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max()
