@@ -743,6 +743,21 @@ def run_ours(args):
         r = pb.fractions(pb.per_launch(pb.g_all, steps), pb.per_launch(pb.g_fwd, steps), pb.per_launch(pb.g_bwd, steps), peak)
         r["mask01"] = alt_mask
         variants["general_affine" if alt_mask == 1.0 else "as_shipped_axis_aligned"] = r
+        if alt_mask == 1.0 and K == 1:
+            # BASELINE configs[1] as literally worded -- grid + sampler on a general affine theta, rotation terms r ~ U(-0.2, 0.2)
+            # as SURVEY.md 8(d) draws them (the workload's own generator), no dropout node -- on the same frames
+            kept = [e["theta"] for e in sets]
+            for i, e in enumerate(sets):
+                e["theta"] = torch.from_numpy(_theta_only(W, wl, 555 + i, B, True)).to(dev)
+            pb.build_graphs(per_set=False)
+            for _ in range(3):
+                pb.g_all.replay()
+            r = pb.fractions(pb.per_launch(pb.g_all, steps), pb.per_launch(pb.g_fwd, steps), pb.per_launch(pb.g_bwd, steps), peak)
+            r["mask01"] = 1.0
+            r["theta"] = "rotated: r01, r10 ~ U(-0.2, 0.2)"
+            variants["general_affine_rotated"] = r
+            for e, t in zip(sets, kept):
+                e["theta"] = t
         pb.mask01 = main_mask
         pb.g_all, pb.g_one, pb.g_fwd, pb.g_bwd, pb.kernels = main_graphs
         if K == 1 and not bf16:

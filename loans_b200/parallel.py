@@ -70,6 +70,7 @@ class GradientAllReduce(object):
         self.is_cuda = self.flat.is_cuda
         self.stream = torch.cuda.Stream(device=device) if self.is_cuda else None
         self._work = None
+        self._avg = False
 
     @property
     def world(self):
@@ -82,10 +83,14 @@ class GradientAllReduce(object):
         if self.world == 1:
             return self
         if self.is_cuda:
+            # NCCL averages inside the collective (ReduceOp.AVG): no separate 1/N pass over the bucket
+            self._avg = dist.get_backend(self.group) == "nccl"
             self.stream.wait_stream(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(self.stream):
-                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM,
+                                             group=self.group, async_op=True)
         else:
+            self._avg = False
             self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         return self
 
@@ -95,7 +100,8 @@ class GradientAllReduce(object):
             self._work = None
             if self.is_cuda:
                 torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
-            self.flat.mul_(1.0 / self.world)
+            if not self._avg:
+                self.flat.mul_(1.0 / self.world)
         if out is not None:
             for v, g in zip(self.views, out):
                 g.copy_(v)
