@@ -612,7 +612,13 @@ def test_frame_ingest_matches_pil_fixtures_and_oracle(T):
         assert np.array_equal(out.cpu().numpy(), g[p + "out_u8"].astype(np.float32) / 255), i
     rng = np.random.default_rng(3)
     for (b, h, w, size) in [(3, 384, 512, (224, 224)), (2, 512, 512, (224, 224)), (2, 224, 224, None), (2, 200, 300, (512, 512)),
-                            (1, 1, 1, (4, 4)), (2, 75, 75, (75, 224))]:
+                            (1, 1, 1, (4, 4)), (2, 75, 75, (75, 224)),
+                            # vertical pass alone on the HWC frame (word-aligned rows, and not), conversion alone with an odd pixel count
+                            (2, 96, 224, (50, 224)), (2, 96, 75, (50, 75)), (2, 75, 75, None),
+                            # crop widths that are no multiple of four, odd frame widths (byte-wise staging), a 1080p frame (53 taps per
+                            # output pixel: coefficient words read from the table, > 48 KiB of staged rows), a single output pixel
+                            (1, 270, 480, (75, 75)), (2, 97, 301, (64, 70)), (1, 1080, 1920, (224, 224)), (1, 33, 47, (1, 1)),
+                            (9, 40, 52, (24, 20))]:
         f = rng.integers(0, 256, (b, h, w, 3), dtype=np.uint8)
         n0 = _lib.launch_count()
         op = FrameIngest(b, (h, w), size)
