@@ -661,3 +661,57 @@ def test_host_buffer_pipeline_with_decoded_uint8_frames(T):
         gt0, _, _ = oc.crop_backward(x, d["theta"], osz, d["gy"], None, 0.0)
         assert np.array_equal(o["y"].numpy(), y0) and np.array_equal(o["grid"].numpy(), g0)
         assert np.abs(o["gtheta"].numpy() - gt0).max() <= 1e-4 * np.abs(gt0).max()
+
+
+def test_device_loader_reads_the_reference_formats(T, tmp_path):
+    """SURVEY 8f rank 4, on-disk side: PNG frames named by `images.csv` / tab-separated `gt.csv` (reference
+    common/datasets/image_dataset.py:48-98, :101-182) through loans_b200.datasets: frames bit for bit what the reference's
+    per-sample sequence gives with the real PIL (decode -> tile -> resize_image -> / 255), boxes scaled as resize_bbox does."""
+    from PIL import Image
+    from loans_b200 import datasets as ds
+    from oracle import ingest_numpy as ig
+    rng = np.random.default_rng(21)
+    root = str(tmp_path)
+    specs = [("a.png", "RGB", (96, 128, 3)), ("b.png", "RGB", (96, 128, 3)), ("c.png", "L", (60, 80)), ("d.png", "RGBA", (96, 128, 4)),
+             ("e.png", "RGB", (50, 50, 3))]
+    raw = {}
+    for name, mode, shape in specs:
+        raw[name] = rng.integers(0, 256, shape, dtype=np.uint8)
+        Image.fromarray(raw[name], mode).save(os.path.join(root, name))
+    with open(os.path.join(root, "images.csv"), "w") as f:
+        f.write("".join(n + "\n" for n, _, _ in specs))
+    with open(os.path.join(root, "gt.csv"), "w") as f:
+        f.write("a.png\t10\t20\t60\t100\nb.png\t0\t0\t96\t128\t5\t6\t50\t60\nc.png\t7\n")
+
+    def reference(name, size):                                        # the reference's get_example, executed with the real PIL
+        with Image.open(os.path.join(root, name)) as fh:
+            image = np.asarray(fh, dtype=np.float32)
+        if image.ndim == 2:
+            image = image[:, :, None]
+        image = image.transpose(2, 0, 1)
+        if image.shape[0] == 1:
+            image = np.tile(image, (3, 1, 1))
+        hwc = np.asarray(Image.fromarray(image.transpose(1, 2, 0).astype('uint8')).convert('RGB'))
+        if size is None:
+            return hwc.transpose(2, 0, 1).astype(np.float32) / 255
+        return ig.pil_reference(hwc[None], size)[0]
+
+    size = (48, 56)
+    d = ds.ImageDataset(os.path.join(root, "images.csv"), root=root, image_size=size)
+    assert len(d) == 5
+    batch = d.get_batch(range(5))                                      # three source sizes in one batch
+    assert tuple(batch.shape) == (5, 3) + size and batch.is_cuda and batch.dtype == T.float32
+    for i, (name, _, _) in enumerate(specs):
+        assert np.array_equal(batch[i].cpu().numpy(), reference(name, size)), name
+        assert np.array_equal(d[i].cpu().numpy(), reference(name, size)), name
+    plain = ds.ImageDataset(["a.png", "e.png"], root=root)              # no resize: sizes differ -> a list
+    out = plain.get_batch([0, 1])
+    assert isinstance(out, list) and np.array_equal(out[1].cpu().numpy(), reference("e.png", None))
+    lab = ds.LabeledImageDataset(os.path.join(root, "gt.csv"), root=root, image_size=size)
+    frames, labels, scores = lab.get_batch([0, 1, 2])
+    assert tuple(frames.shape) == (3, 3) + size and scores.shape == (3, 1)
+    assert np.array_equal(frames[1].cpu().numpy(), reference("b.png", size))
+    assert labels[0].dtype == np.int32 and labels[0].tolist() == [[5, 8, 30, 43]]          # 10*48/96, 20*56/128, 60/2, 100*.4375
+    assert labels[1].tolist() == [[0, 0, 48, 56], [2, 2, 25, 26]] and labels[2].tolist() == [7]
+    img, label, dummy = lab[0]
+    assert np.array_equal(img.cpu().numpy(), reference("a.png", size)) and label.tolist() == labels[0].tolist() and dummy.shape == (1,)
