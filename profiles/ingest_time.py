@@ -1,5 +1,5 @@
 """Device time of the frame ingest (loans_stn_ingest_u8) over rotating buffers, CUDA-graph replay: resize 384x512 -> 224x224,
-the conversion alone at 224x224, and a 1080p source.  usage: ingest_time.py [path/to/libloans_stn.so ...] (default: the product)"""
+the conversion alone at 224x224, and a 1080p source.  usage: ingest_time.py [path/to/libloans_stn.so] (default: the product)"""
 import json
 import os
 import sys
@@ -8,7 +8,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
+from loans_b200 import _lib  # noqa: E402
 from loans_b200.functions import FrameIngest  # noqa: E402
+
+if len(sys.argv) > 1:
+    _lib.LIB_PATH = os.path.abspath(sys.argv[1])                       # an A/B build (profiles/ab_local.sh)
 
 dev = torch.device("cuda", 0)
 CASES = [("384x512->224x224 x64", 64, (384, 512), (224, 224)), ("224x224 convert x64", 64, (224, 224), None),
@@ -35,4 +39,4 @@ for name, b, src, dst in CASES:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (20 * S)
     nb = b * src[0] * src[1] * 3 + 4 * b * 3 * oh * ow
-    print(json.dumps({"case": name, "us": round(us, 2), "algorithmic_bytes": nb, "gbs": round(nb / us / 1e3, 1)}), flush=True)
+    print(json.dumps({"lib": os.path.basename(_lib.LIB_PATH), "case": name, "us": round(us, 2), "algorithmic_bytes": nb, "gbs": round(nb / us / 1e3, 1)}), flush=True)
