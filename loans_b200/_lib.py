@@ -18,6 +18,7 @@ CFG_PDL = 8
 CFG_BAND_CS, CFG_BAND_ROWS, CFG_BAND_TILE_KB, CFG_BAND_VARIANT = 4, 5, 6, 7
 # ... and A/B switches of a -DSTN_DEVEL build (the product build answers them with an error)
 CFG_TMA_FORWARD = 2
+CFG_KFRAME_ROWS = 13
 CFG_THETA_FIRST = 9
 
 _lib = None
@@ -117,6 +118,11 @@ def band_tuning(cs=0, rows=0, tile_kb=0, variant=0):
     """A/B knobs of the band kernel (0 = automatic): CTAs per crop, crop rows per band, tile budget, kernel variant."""
     for key, val in ((CFG_BAND_CS, cs), (CFG_BAND_ROWS, rows), (CFG_BAND_TILE_KB, tile_kb), (CFG_BAND_VARIANT, variant)):
         check(lib().loans_stn_configure(key, int(val)), "loans_stn_configure")
+
+
+def kframe_rows(rows=0):
+    """Frame rows per CTA of the several-crops-per-frame gx kernel (0 = automatic)."""
+    check(lib().loans_stn_configure(CFG_KFRAME_ROWS, int(rows)), "loans_stn_configure")
 
 
 def launch_count():

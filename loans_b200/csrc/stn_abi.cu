@@ -94,6 +94,8 @@ int launch_crop_bwd(CropParams p, int gy_dtype, cudaStream_t stream);
 int launch_sep_fwd(CropParams p, int y_dtype, cudaStream_t stream);
 #endif
 int launch_crop_bwd_band(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement);   // -1: use the general kernel
+int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement); // -1: use the general kernel
+void kframe_tuning(int rows);
 void band_tuning(int which, int value);
 int launch_crop_bwd_theta_tab(CropParams p, int gy_dtype, cudaStream_t stream);   // -1: not taken
 int launch_prepare_images(const float *x, float *out, float scale, int b, int h, int w, cudaStream_t stream);      // -1: shape not supported, use the general kernel
@@ -177,9 +179,12 @@ static int crop_bwd_dispatch(const CropParams &p, bool upright, int gy_dtype, cu
             const int rc = launch_crop_bwd_band(p, gy_dtype, stream, band < 0);
             if (rc >= 0) return rc;
         }
-        // several crops per frame with gx wanted stay with the general kernel: three axis-aligned designs for that case
-        // (warp-owned frame-row windows, a per-window work queue, CTA-owned bands with crop-sequential phases) all measured
-        // slower than it at BASELINE config 4 (profiles/README.md, round 2)
+        // several crops per frame, gx wanted: warp-owned frame rows, each crop row found through an inverse row map and added
+        // from gy and the table weights alone; gtheta by the table-driven theta kernel in front of it (stn_kframe.cu)
+        if (p.gx != nullptr && p.K > 1) {
+            const int rc = launch_crop_bwd_kframe(p, gy_dtype, stream, band < 0);
+            if (rc >= 0) return rc;
+        }
     }
     return launch_crop_bwd(p, gy_dtype, stream);
 }
@@ -216,6 +221,11 @@ int loans_stn_configure(int key, int value)
     if (key >= LOANS_STN_CFG_BAND_CS && key <= LOANS_STN_CFG_BAND_VARIANT) {          // test hooks (loans_stn_devel.h)
         if (value < 0) return set_error("loans_stn_configure: key %d needs a value >= 0", key);
         band_tuning(key - LOANS_STN_CFG_BAND_CS, value);
+        return 0;
+    }
+    if (key == LOANS_STN_CFG_KFRAME_ROWS) {
+        if (value < 0) return set_error("loans_stn_configure: key %d needs a value >= 0", key);
+        kframe_tuning(value);
         return 0;
     }
 #ifdef STN_DEVEL

@@ -56,6 +56,9 @@ struct CropParams {
     int band_tile_bytes, band_zero_bytes, band_region_bytes;   // region = tile + zero plane, or the general roles' warp tiles
     int band_flags;                                             // A/B switches (bit 0: zero rows stored early, bit 1: no L2 prefetch of the taps)
     int band_fb_tiles_per_warp;                                 // declined crops: tiles per warp in the general gx role
+    // several crops per frame, gx of axis-aligned crops (stn_kframe.cu): kf_ctas_per_frame CTAs per frame, kf_rows_cta frame
+    // rows each; the region holds the warps' row buffers (or the general role's warp tiles)
+    int kf_rows_cta, kf_ctas_per_frame, kf_region_bytes;
 };
 
 // Channels-last crop pixel with the channel count padded to four (LOANS_STN_FLAG_NHWC4: c == 3, bf16): y / gy are

@@ -224,12 +224,13 @@ def test_axis_aligned_kernels_are_bitwise_the_general_kernels(G, name, batch):
         y1, g1 = G.crop_fwd(d["x"], d["theta"], osz, 0.0, k)
         _lib.band_backward(True)
         b1 = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
-        assert _lib.last_kernel() in (("stn_bwd_band_kernel/row", "stn_bwd_band_kernel/cta") if k == 1 else ("stn_bwd_kernel",))
+        assert _lib.last_kernel() in (("stn_bwd_band_kernel/row", "stn_bwd_band_kernel/cta") if k == 1
+                                      else ("stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel",))
     finally:
         _lib.band_backward(None)
         if devel:
             _lib.tma_forward(False)
-    assert _lib.launch_count() - n0 == 2
+    assert _lib.launch_count() - n0 == (2 if k == 1 else 3)          # several crops per frame: gtheta and gx are two kernels
     assert np.array_equal(y0, y1) and np.array_equal(g0, g1)
     assert np.array_equal(b0[2], b1[2])                                   # ggrid bit-exact
     assert G.rel_max(b1[1], b0[1]) <= 2e-6 and G.rel_max(b1[0], b0[0]) <= 1e-5
@@ -361,6 +362,53 @@ def test_band_backward_full_size_adjoint(G):
 
 
 # ------------------------------------------------------------------------------------------------ frames without grad
+# ------------------------------------------------------------------------------------------------ several crops per frame
+@pytest.mark.parametrize("rows", [0, 8, 16, 1000])         # frame rows per CTA: automatic, shortest, two passes per warp, whole frame
+@pytest.mark.parametrize("shape,k", [((3, 24, 24, 9, 9), 4), ((3, 96, 128, 75, 75), 4), ((1, 40, 64, 5, 33), 2), ((4, 64, 48, 6, 70), 8),
+                                     ((3, 32, 16, 1, 5), 4), ((3, 20, 12, 7, 1), 2)])
+def test_kframe_backward_hard_boxes(G, shape, k, rows):
+    """Several crops per frame with gx (stn_kframe.cu: warp-owned frame rows, inverse row map): frames whose crops all step by
+    >= 2 frame pixels (taken), frames with an up-sampling / mirrored / rotated / zero-scale crop (declined: the general gx role
+    in the same launch), boxes hanging out of the frame on every side, crops sharing frame rows -- against the oracle."""
+    from loans_b200 import _lib
+    c, h, w, oh, ow = shape
+    rng = np.random.default_rng(sum(shape) + k)
+    # frames 0..: all down-sampling boxes (taken); then the hard boxes of the band tests, k per frame (mostly declined)
+    easy = []
+    for _ in range(3 * k):
+        s = rng.uniform(0.55, 1.2, 2) * np.array([max(2.2 * (ow - 1) / (w - 1), 0.3), max(2.2 * (oh - 1) / (h - 1), 0.3)])
+        t = rng.uniform(-0.7, 0.7, 2)
+        easy.append([[s[0], 0, t[0]], [0, s[1], t[1]]])
+    theta = np.concatenate([np.array(easy, np.float32), BAND_THETAS[:(len(BAND_THETAS) // k) * k]])
+    x = rng.random((len(theta) // k, c, h, w), dtype=np.float32)
+    try:
+        _lib.kframe_rows(rows)
+        _full_check(G, x, theta, (oh, ow), 0.0, k, seed=13)
+        assert _lib.last_kernel() == "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel"
+    finally:
+        _lib.kframe_rows(0)
+
+
+def test_kframe_backward_at_cfg4_size(G):
+    """BASELINE config 4 with the automatic dispatch (mask 0, 16 jittered boxes per frame): 24 of its 128 frames at full frame and
+    crop size, every frame against the C oracle; run-to-run bit reproducibility."""
+    from loans_b200 import _lib
+    wl = W.WORKLOADS["cfg4"]
+    d = W.make_inputs(wl, batch=24, rotate=False, with_ggrid=True)
+    osz = (wl.out_h, wl.out_w)
+    k = wl.crops_per_frame
+    gt, gx, ggo = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    assert _lib.last_kernel() == "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel"
+    gt2, gx2, _ = G.crop_bwd(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    assert np.array_equal(gx, gx2) and np.array_equal(gt, gt2)
+    gt0, gx0, gg0 = oc.crop_backward(d["x"], d["theta"], osz, d["gy"], d["ggrid"], 0.0, k)
+    assert np.array_equal(ggo, gg0)
+    per_frame = np.abs(gx - gx0).reshape(24, -1).max(axis=1) / np.abs(gx0).reshape(24, -1).max(axis=1)
+    assert per_frame.max() <= 2e-6, per_frame.max()
+    sc = np.abs(gt0).reshape(24 * k, -1).max(axis=1)[:, None, None]
+    assert (np.abs(gt - gt0) <= GRAD_TOL * sc).all()
+
+
 @pytest.mark.parametrize("name,batch,bf16", [("cfg1", None, False), ("cfg2", 16, False), ("cfg3", 6, True), ("cfg4", 3, False), ("cfg5", 24, False)])
 def test_theta_gradient_without_gx_table_kernel(G, name, batch, bf16):
     """gx == NULL with the rotation terms masked (every LoANs call): the table-driven theta kernel -- any number of crops per
