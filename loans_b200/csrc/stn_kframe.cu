@@ -115,7 +115,11 @@ __global__ void __launch_bounds__(kThreads, 3) stn_bwd_kframe_kernel(const __gri
 
     const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
     pdl_launch_dependents();
-    const int b = blockIdx.x / p.kf_ctas_per_frame, part = blockIdx.x - b * p.kf_ctas_per_frame;
+    // bands in the middle of a frame carry most crop rows, the ones at its top and bottom few or none: the grid walks the bands
+    // centre-out (all frames' middle bands first), so that the light bands fill the tail of the last wave
+    const int frames = p.N / p.K;
+    const int order = blockIdx.x / frames, b = blockIdx.x - order * frames;
+    const int part = (p.kf_ctas_per_frame - 1) / 2 + ((order & 1) ? (order + 1) / 2 : -(order / 2));
     const int rows = p.kf_rows_cta;
     const int r0 = part * rows, nr = min(rows, H - r0);                 // the band: frame rows [r0, r0 + nr)
     {   // zero the row buffers: needs no input, overlaps the tail of the previous kernel
@@ -337,11 +341,13 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
         p.gx_tile_bytes = (int)(sizeof(float) * (size_t)p.C * tr * tw * kWarps);
         p.gx_vec4 = 1; p.gx_tma_store = 0; p.gx_zero_bytes = 0;
     }
-    // frame rows per CTA: a multiple of the warps per CTA, about 2.5 waves of CTAs (three per SM) over the machine -- the
-    // tables of all the frame's crops are built once per CTA, so bands should not be shorter than they have to
+    // frame rows per CTA: a multiple of the warps per CTA, a little over ONE wave of CTAs (three per SM) over the machine.  The
+    // tables of all the frame's crops are built once per CTA, so long bands are cheaper; the grid walks the bands centre-out, so
+    // the few CTAs behind the first wave are the light top / bottom bands.  Measured at BASELINE config 4 (128 frames, backward
+    // incl. the theta kernel): 312 / 302 us with 128 / 136 rows (4 CTAs per frame), 360 us with 120 (5), 333-350 us with 16 ... 104
     int rows = g_kf_rows;
     if (rows <= 0) {
-        long long per_frame = (5LL * 3 * num_sms() / 2 + frames - 1) / frames;          // CTAs per frame wanted
+        long long per_frame = (long long)(1.15 * 3.0 * num_sms() / (double)frames + 0.5);        // CTAs per frame wanted
         if (per_frame < 1) per_frame = 1;
         rows = (int)((p.H + per_frame - 1) / per_frame);
         rows = (rows + kWarps - 1) / kWarps * kWarps;
