@@ -16,10 +16,12 @@ if len(sys.argv) > 2:
     _lib.LIB_PATH = os.path.abspath(sys.argv[2])
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 wl = W.WORKLOADS[name]._replace(rotation_ratio=0.0)
+if os.environ.get("KF_BATCH"):
+    wl = wl._replace(batch=int(os.environ["KF_BATCH"]))
 B, K, C, H, Wd, oH, oW = wl.batch, wl.crops_per_frame, wl.channels, wl.height, wl.width, wl.out_h, wl.out_w
 N = B * K
 dev = torch.device("cuda", 0)
-S = 2
+S = 2 if wl.batch >= 64 else 8
 sets = []
 for s in range(S):
     d = W.make_inputs(wl, seed=70 + s)

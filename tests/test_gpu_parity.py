@@ -383,9 +383,11 @@ def test_kframe_backward_hard_boxes(G, shape, k, rows):
     x = rng.random((len(theta) // k, c, h, w), dtype=np.float32)
     try:
         _lib.kframe_rows(rows)
+        _lib.band_backward(True)                      # wherever it applies (the automatic rule takes it from 16 frames)
         _full_check(G, x, theta, (oh, ow), 0.0, k, seed=13)
         assert _lib.last_kernel() == "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel"
     finally:
+        _lib.band_backward(None)
         _lib.kframe_rows(0)
 
 
