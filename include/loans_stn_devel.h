@@ -7,6 +7,8 @@
  *   LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: CTAs per crop, crop rows per band, shared-memory tile budget in
  *   KiB, kernel variant (1: CTA bands, 3: row bands) of the band backward; 0 = automatic.
  *   LOANS_STN_CFG_KFRAME_ROWS: frame rows per CTA of the several-crops-per-frame gx kernel (stn_kframe.cu); 0 = automatic.
+ *   LOANS_STN_CFG_KFRAME_SINGLE != 0: that kernel (theta kernel + row-owner gx) also for ONE crop per frame, ahead of the band
+ *     backward (A/B arm).
  *
  * Only in a -DSTN_DEVEL build (make -C loans_b200/csrc EXTRA=-DSTN_DEVEL; the product build answers them with an error):
  *   LOANS_STN_CFG_TMA_FORWARD != 0: forward of axis-aligned crops (mask01 == 0, w % 4 == 0) through the AxisTap-table +
@@ -31,6 +33,7 @@
 #define LOANS_STN_CFG_THETA_ONLY_KERNEL 11
 #define LOANS_STN_CFG_FWD_PX_PER_CTA 12
 #define LOANS_STN_CFG_KFRAME_ROWS 13
+#define LOANS_STN_CFG_KFRAME_SINGLE 14
 
 /* measurement aid of bench.py's "floor" block (stn_probe.cu): what a kernel of our launch shape costs before any STN
  * arithmetic -- mode 0 an empty kernel with our launch attributes, mode 1 two dependent DRAM round trips and a store,

@@ -163,6 +163,7 @@ static CropParams base_params(int n, int k, int c, int h, int w, int oh, int ow)
 // zeroed the rotation terms) that the crops are axis-aligned boxes.  It only SELECTS the kernels written for that case;
 // every one of them checks each crop's own rotation terms on the device and runs the general roles for a crop that is
 // rotated after all, inside the same launch -- a wrong hint costs time, never correctness.
+static std::atomic<bool> g_kf_single{false};
 static int crop_bwd_dispatch(const CropParams &p, bool upright, int gy_dtype, cudaStream_t stream)
 {
     const int band = g_band_backward.load();
@@ -175,6 +176,14 @@ static int crop_bwd_dispatch(const CropParams &p, bool upright, int gy_dtype, cu
         // one crop per frame, gx wanted: the band backward -- every crop pixel evaluated once, gx written once by the band
         // that owns the frame rows (stn_band.cu).  By default it is taken where it measured faster than the general kernel
         // (rule in launch_crop_bwd_band); LOANS_STN_CFG_BAND_BACKWARD = 1 / 0 forces it on (wherever it applies) / off
+        // one crop per frame on WIDE frame rows (>= 4 KiB per row group, e.g. 512-px RGB frames): the two-kernel path of
+        // stn_kframe.cu -- gtheta by the table-driven theta kernel, gx by warp-owned frame rows from gy and the table weights
+        // alone -- measured faster than the CTA bands (172 vs 190 us at BASELINE config 3); narrow frames stay with the row
+        // bands (cfg2: 28 vs 17 us, cfg5: 319 vs 229 us).  LOANS_STN_CFG_KFRAME_SINGLE forces it for any width (A/B arm)
+        if (p.gx != nullptr && p.K == 1 && (g_kf_single.load() || (band < 0 && sizeof(float) * (size_t)p.W * p.C >= 4096))) {
+            const int rc = launch_crop_bwd_kframe(p, gy_dtype, stream, band < 0 && !g_kf_single.load());
+            if (rc >= 0) return rc;
+        }
         if (p.gx != nullptr && p.K == 1) {
             const int rc = launch_crop_bwd_band(p, gy_dtype, stream, band < 0);
             if (rc >= 0) return rc;
@@ -223,6 +232,7 @@ int loans_stn_configure(int key, int value)
         band_tuning(key - LOANS_STN_CFG_BAND_CS, value);
         return 0;
     }
+    if (key == LOANS_STN_CFG_KFRAME_SINGLE) { g_kf_single.store(value != 0); return 0; }
     if (key == LOANS_STN_CFG_KFRAME_ROWS) {
         if (value < 0) return set_error("loans_stn_configure: key %d needs a value >= 0", key);
         kframe_tuning(value);

@@ -322,7 +322,7 @@ void kframe_tuning(int rows) { g_kf_rows = rows; }
 // unaligned rows): the caller then launches the general kernel.  Two launches: gtheta (table-driven theta kernel), then gx.
 int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool by_measurement)
 {
-    if (!p.gx || p.K < 2) return -1;
+    if (!p.gx || p.K < 1) return -1;
     // measured against the general kernel at BASELINE config 4's shapes: 128 us vs 155 us with 32 frames, 311-349 vs 541 us with
     // 128; 50 vs 45 us with 8 frames and 32 vs 29 us with 2 (two launches, tables of every crop per CTA): taken from 16 frames
     if (by_measurement && p.N / p.K < 16) return -1;
@@ -352,8 +352,11 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
         long long per_frame = (long long)(1.15 * 3.0 * num_sms() / (double)frames + 0.5);        // CTAs per frame wanted
         if (per_frame < 1) per_frame = 1;
         rows = (int)((p.H + per_frame - 1) / per_frame);
+        // ... but no longer than the tables ask for: with few crops per frame they are cheap and short bands balance better
+        // (one crop per frame, config 3: 172 us with 16 / 32 rows, 177 with 64, 184 with 112, 208 with 256)
+        if (rows > 8 * p.K) rows = 8 * p.K;
+        if (rows < 4 * kWarps) rows = 4 * kWarps;
         rows = (rows + kWarps - 1) / kWarps * kWarps;
-        if (rows < 2 * kWarps) rows = 2 * kWarps;
     }
     if (rows > p.H) rows = p.H;
     p.kf_rows_cta = rows;

@@ -25,14 +25,14 @@ S = 2 if wl.batch >= 64 else 8
 sets = []
 for s in range(S):
     d = W.make_inputs(wl, seed=70 + s)
-    sets.append({"x": torch.from_numpy(d["x"]).to(dev), "th": torch.from_numpy(d["theta"]).to(dev), "gy": torch.from_numpy(d["gy"]).to(dev),
+    sets.append({"x": torch.from_numpy(d["x"]).to(dev), "th": torch.from_numpy(d["theta"]).to(dev), "gy": torch.from_numpy(d["gy"]).to(dev).to(torch.bfloat16 if wl.out_dtype == "bf16" else torch.float32),
                  "gt": torch.empty((N, 2, 3), device=dev), "gx": torch.empty((B, C, H, Wd), device=dev)})
 L = _lib.lib()
 
 
 def bwd(e, gx=True):
     _lib.check(L.loans_stn_crop_bwd(e["x"].data_ptr(), e["th"].data_ptr(), 0.0, e["gy"].data_ptr(), None, e["gt"].data_ptr(),
-                                    e["gx"].data_ptr() if gx else None, None, N, K, C, H, Wd, oH, oW, _lib.F32,
+                                    e["gx"].data_ptr() if gx else None, None, N, K, C, H, Wd, oH, oW, _lib.BF16 if wl.out_dtype == "bf16" else _lib.F32,
                                     torch.cuda.current_stream().cuda_stream), "crop_bwd")
 
 
@@ -59,10 +59,19 @@ _lib.force_general(True)
 timed(bwd, "general kernel")
 _lib.force_general(False)
 timed(lambda e: bwd(e, False), "theta only (no gx)")
-for rows in [int(v) for v in os.environ.get("KF_ROWS", "0,16,32,64,128,256").split(",")]:
+for rows in [int(v) for v in os.environ.get("KF_ROWS", "0,16,32,64,128,256").split(",")] if K > 1 else []:
     _lib.kframe_rows(rows)
     timed(bwd, "theta + kframe, rows per CTA %d" % rows)
 _lib.kframe_rows(0)
+if K == 1:
+    timed(bwd, "band backward (automatic rule)")
+    L.loans_stn_configure(14, 1)
+    for rows in [int(v) for v in os.environ.get("KF_ROWS", "0").split(",")]:
+        _lib.kframe_rows(rows)
+        timed(bwd, "theta + kframe on one crop per frame, rows per CTA %d" % rows)
+    _lib.kframe_rows(0)
+    L.loans_stn_configure(14, 0)
+    sys.exit(0)
 L.loans_stn_configure(1, 0)                      # LOANS_STN_CFG_PDL off
 timed(bwd, "theta + kframe, no programmatic dependent launch")
 L.loans_stn_configure(1, 1)

@@ -490,7 +490,7 @@ def test_reference_gpu_kernels_agree_with_oracle_and_cuda_path(G, name, batch, m
 # ------------------------------------------------------------------------------------------------ the benched dispatch, full size
 @pytest.mark.parametrize("name,need_gx,kernel", [("cfg2", True, "stn_bwd_band_kernel/row"), ("cfg2", False, "stn_bwd_theta_tab_kernel"),
                                                  ("cfg5", True, "stn_bwd_band_kernel/row"), ("cfg5", False, "stn_bwd_theta_tab_kernel"),
-                                                 ("cfg3", True, "stn_bwd_band_kernel/cta")])
+                                                 ("cfg3", True, "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel")])
 def test_benched_dispatch_at_full_size_against_the_oracle(G, name, need_gx, kernel):
     """bench.py's headline (cfg2, batch 64) and its `configs` block (cfg5 batch 1024 -- two CTAs per crop --, cfg3) with the
     AUTOMATIC dispatch rule, as LoANs ships the path (mask 0): which kernel ran is asserted, and EVERY frame is compared with
