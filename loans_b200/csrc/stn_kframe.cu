@@ -37,44 +37,6 @@ struct alignas(8) KfCol {             // one crop column / row: weight of tap id
     int code;
 };
 
-struct KfCrop {                       // one crop of the frame
-    float t00, t01, t02, t10, t11, t12;   // masked theta
-    int ok;                           // the crop is taken by this path
-    int rmin, rmax;                   // unpadded frame rows any tap of the crop can touch (conservative)
-};
-
-// (idx0 + 1) - c and 1 - (c - idx0) are the same real number and both exactly representable (c - idx0 is exact and a
-// multiple of ulp(c)), so the second tap weight follows from the first without a rounding of its own
-__device__ __forceinline__ float kf_w1(float w0) { return f_sub(1.0f, w0); }
-
-__device__ __forceinline__ KfCrop make_kf_crop(const Theta &th, int H, int W, int oH, int oW)
-{
-    KfCrop c;
-    c.t00 = th.t00; c.t01 = th.t01; c.t02 = th.t02; c.t10 = th.t10; c.t11 = th.t11; c.t12 = th.t12;
-    c.ok = 0;
-    c.rmin = 0; c.rmax = -1;
-    if (!(th.t01 == 0.0f && th.t10 == 0.0f)) return c;                 // rotation terms must be masked to (+-)0
-    if (!(th.t00 > 0.0f && th.t11 > 0.0f)) return c;                   // mirrored or degenerate boxes (and NaN): general role
-    const float sx = oW > 1 ? 2.0f / (float)(oW - 1) : 0.0f, sy = oH > 1 ? 2.0f / (float)(oH - 1) : 0.0f;
-    const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);
-    const float muj = th.t00 * sx * hw, mvi = th.t11 * sy * hh;         // frame pixels per crop pixel
-    const float cu = (th.t02 - th.t00 + 1.0f) * hw + 1.0f, cv = (th.t12 - th.t11 + 1.0f) * hh + 1.0f;
-    const float nj = (float)(oW > 1 ? oW - 1 : 1), ni = (float)(oH > 1 ? oH - 1 : 1);
-    const float mag = muj * nj + fabsf(cu) + mvi * ni + fabsf(cv) + (float)(W + H);
-    if (!(mag < 1e6f)) return c;                                       // also NaN / inf
-    // two crop pixels share a frame pixel only if their coordinates differ by less than 2; T adds the float32 slack
-    const float slack = 0.05f + 1e-5f * mag;
-    const float T = (2.0f + 2.0f * slack) * 1.001f;
-    if (oW > 1 && muj < T) return c;
-    if (oH > 1 && mvi < T) return c;
-    c.ok = 1;
-    const float v_a = cv, v_b = cv + mvi * ni, m = 2.0f + slack;
-    // padded coordinate p touches unpadded rows floor(p) - 1 and floor(p)
-    c.rmin = f_floor_i(fmaxf(fminf(v_a, v_b) - m - 1.0f, -4.0f));
-    c.rmax = f_ceil_i(fminf(fmaxf(v_a, v_b) + m, 2.0e9f));
-    return c;
-}
-
 // A frame with a crop this path does not take: the whole frame through the general gx role (same result, any theta).
 // xs / ys / geom alias the (not yet built) tables, not the crops.  Out of line: the general role's registers are its own.
 template <typename GT, int CG, bool GRAY>

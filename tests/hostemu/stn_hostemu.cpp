@@ -324,4 +324,83 @@ long long emu_band_bwd(const float *x, const float *theta, float mask01, const f
     return conflicts;
 }
 
+// The row-owner gx kernel of stn_kframe.cu (several crops per frame), executed serially with the kernel's own planning code
+// (make_kf_crop, make_band_axis): per frame the verdict of every crop, the inverse row map, then frame row by frame row the crop
+// rows on it in ascending crop order, gy * wu * wv added into a row buffer in the kernel's order.  ok[b] = 1 where the frame is
+// taken (every crop passes); other frames are left untouched.  Returns the number of buffer addresses two columns of ONE crop
+// row wrote (a race between the lanes of a warp on the GPU); stats[0] = inverse-row-map slots written twice (two crop rows of
+// one crop on one frame row: the assumption the kernel rests on), stats[1] = frames taken.
+long long emu_kframe_gx(const float *theta, float mask01, const float *gy, float *gx, int *ok,
+                        int n, int k, int c, int h, int w, int oh, int ow, long long *stats)
+{
+    const double xstep = ow > 1 ? 2.0 / (ow - 1) : 0.0, ystep = oh > 1 ? 2.0 / (oh - 1) : 0.0;
+    const int npx = oh * ow, frames = n / k;
+    const size_t plane = (size_t)h * w;
+    long long conflicts = 0;
+    stats[0] = stats[1] = 0;
+    std::vector<KfCrop> crops(k);
+    std::vector<BandAxis> coltab((size_t)k * ow), rowtab((size_t)k * oh);
+    std::vector<int> rowinv((size_t)k * h);
+    std::vector<float> buf((size_t)c * w);
+    std::vector<int> stamp((size_t)c * w);
+    int stamp_id = 0;
+    for (int b = 0; b < frames; ++b) {
+        bool all = true;
+        for (int kk = 0; kk < k; ++kk) {
+            crops[kk] = make_kf_crop(load_theta_masked(theta + 6 * ((size_t)b * k + kk), mask01), h, w, oh, ow);
+            all = all && crops[kk].ok;
+        }
+        ok[b] = all;
+        if (!all) continue;
+        stats[1]++;
+        std::fill(rowinv.begin(), rowinv.end(), -1);
+        for (int kk = 0; kk < k; ++kk) {
+            const KfCrop &cr = crops[kk];
+            for (int j = 0; j < ow; ++j) coltab[(size_t)kk * ow + j] = make_band_axis(cr.t00, cr.t01, cr.t02, linspace_pm1(j, ow, xstep), true, w);
+            for (int i = 0; i < oh; ++i) {
+                const BandAxis a = make_band_axis(cr.t11, cr.t10, cr.t12, linspace_pm1(i, oh, ystep), false, h);
+                rowtab[(size_t)kk * oh + i] = a;
+                const int t0 = (a.code & kAxIdxMask) - 1;
+                if ((a.code & kAxTap0) && t0 >= 0 && t0 < h) { if (rowinv[(size_t)kk * h + t0] >= 0) stats[0]++; rowinv[(size_t)kk * h + t0] = 2 * i; }
+                if ((a.code & kAxTap1) && t0 + 1 >= 0 && t0 + 1 < h) { if (rowinv[(size_t)kk * h + t0 + 1] >= 0) stats[0]++; rowinv[(size_t)kk * h + t0 + 1] = 2 * i + 1; }
+            }
+        }
+        float *gxb = gx + (size_t)b * c * plane;
+        for (int r = 0; r < h; ++r) {
+            std::fill(buf.begin(), buf.end(), 0.f);
+            for (int kk = 0; kk < k; ++kk) {
+                const int cur = rowinv[(size_t)kk * h + r];
+                if (cur < 0) continue;
+                const int i = cur >> 1;
+                const BandAxis &rw = rowtab[(size_t)kk * oh + i];
+                const float wv = (cur & 1) ? rw.w0 : kf_w1(rw.w0);
+                const float *gyc = gy + ((size_t)b * k + kk) * c * npx + (size_t)i * ow;
+                ++stamp_id;
+                for (int j = 0; j < ow; ++j) {
+                    const BandAxis &col = coltab[(size_t)kk * ow + j];
+                    const int u = (col.code & kAxIdxMask) - 1;
+                    for (int ch = 0; ch < c; ++ch) {
+                        const float g = gyc[(size_t)ch * npx + j];
+                        if (col.code & kAxTap0) {
+                            const int o = ch * w + u;
+                            if (stamp[o] == stamp_id) ++conflicts;
+                            stamp[o] = stamp_id;
+                            buf[o] = f_add(buf[o], f_mul(f_mul(g, kf_w1(col.w0)), wv));
+                        }
+                        if (col.code & kAxTap1) {
+                            const int o = ch * w + u + 1;
+                            if (stamp[o] == stamp_id) ++conflicts;
+                            stamp[o] = stamp_id;
+                            buf[o] = f_add(buf[o], f_mul(f_mul(g, col.w0), wv));
+                        }
+                    }
+                }
+            }
+            for (int ch = 0; ch < c; ++ch)
+                for (int col = 0; col < w; ++col) gxb[(size_t)ch * plane + (size_t)r * w + col] = buf[(size_t)ch * w + col];
+        }
+    }
+    return conflicts;
+}
+
 }  // extern "C"

@@ -268,3 +268,57 @@ def test_band_backward_declines_rotations(emu):
     check_band(emu, x, _theta([[[0.7, 0.1, 0], [0, 0.7, 0]]]), (8, 8), 1.0, expect_ok=[False], layouts=((2, 8),))
     check_band(emu, x, _theta([[[0.7, 0.1, 0], [0, 0.7, 0]]]), (8, 8), 0.0, expect_ok=[True], layouts=((2, 8),))
     check_band(emu, x, _theta([[[np.nan, 0, 0], [0, 0.7, 0]]]), (8, 8), 0.0, expect_ok=[False], layouts=((2, 8),))
+
+
+# ------------------------------------------------------------------------------------------------ several crops per frame
+def run_kframe(lib, theta, osz, gy, x_shape, k):
+    b, c, h, w = x_shape
+    n = theta.shape[0]
+    oh, ow = osz
+    lib.emu_kframe_gx.argtypes = [_f, ctypes.c_float, _f, _f, ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 7 + [ctypes.POINTER(ctypes.c_longlong)]
+    lib.emu_kframe_gx.restype = ctypes.c_longlong
+    gx = np.full((b, c, h, w), np.nan, np.float32)
+    ok = np.zeros(b, np.int32)
+    stats = (ctypes.c_longlong * 2)()
+    conflicts = lib.emu_kframe_gx(_p(theta), 0.0, _p(gy), _p(gx), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n, k, c, h, w, oh, ow, stats)
+    return gx, ok.astype(bool), conflicts, stats[0], stats[1]
+
+
+@pytest.mark.parametrize("shape,k", [((3, 40, 48, 9, 9), 4), ((3, 96, 128, 25, 31), 3), ((1, 33, 20, 5, 7), 2), ((3, 224, 224, 75, 75), 2)])
+def test_kframe_plan_near_the_step_threshold(emu, shape, k):
+    """The row-owner gx kernel (stn_kframe.cu) rests on one assumption: a crop it takes (make_kf_crop: steps of >= ~2 frame pixels)
+    puts at most one crop row on a frame row and at most one crop column of a row on a frame column.  Random boxes whose steps
+    straddle the threshold (1.7 ... 2.6 frame pixels per crop pixel), hanging out of the frame on every side: no inverse-map slot
+    written twice, no buffer address written twice within a crop row, gx of the taken frames equal to the oracle's."""
+    c, h, w, oh, ow = shape
+    rng = np.random.default_rng(sum(shape) * 7 + k)
+    frames = 48
+    n = frames * k
+    step = rng.uniform(1.7, 2.6, (n, 2))
+    near = rng.uniform(2.1, 2.4, (n, 2))                                # just above (or on) the threshold: the delicate side
+    every_other = (np.arange(n) // k) % 2 == 0
+    step[every_other] = near[every_other]
+    theta = np.zeros((n, 2, 3), np.float32)
+    theta[:, 0, 0] = step[:, 0] * max(ow - 1, 1) / (w - 1)
+    theta[:, 1, 1] = step[:, 1] * max(oh - 1, 1) / (h - 1)
+    theta[:, :, 2] = rng.uniform(-0.9, 0.9, (n, 2))
+    theta[::(11 * k)] *= np.float32(1.7)                                # some clearly down-sampling ones
+    x = rng.random((frames, c, h, w), dtype=np.float32)
+    gy = rng.standard_normal((n, c, oh, ow), dtype=np.float32)
+    gx, ok, conflicts, dup_rows, taken = run_kframe(emu, theta, (oh, ow), gy, x.shape, k)
+    assert conflicts == 0 and dup_rows == 0
+    assert 0 < taken < frames or k == 1                                 # both verdicts occur
+    _, gx0, _ = oc.crop_backward(x, theta, (oh, ow), gy, None, 0.0, k)
+    assert ok.sum() == taken
+    sc = np.abs(gx0[ok]).max()
+    assert np.abs(gx[ok] - gx0[ok]).max() <= 2e-6 * sc
+
+
+def test_kframe_plan_on_the_assessor_feed(emu):
+    """BASELINE config 4's box distribution (16 jittered boxes per frame) at a reduced frame size: every frame is taken."""
+    wl = W.WORKLOADS["cfg4"]._replace(height=160, width=160, out_h=25, out_w=25)
+    d = W.make_inputs(wl, batch=6, rotate=False)
+    gx, ok, conflicts, dup_rows, taken = run_kframe(emu, d["theta"], (25, 25), d["gy"], d["x"].shape, wl.crops_per_frame)
+    assert conflicts == 0 and dup_rows == 0 and taken == 6
+    _, gx0, _ = oc.crop_backward(d["x"], d["theta"], (25, 25), d["gy"], None, 0.0, wl.crops_per_frame)
+    assert np.abs(gx - gx0).max() <= 2e-6 * np.abs(gx0).max()
