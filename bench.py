@@ -575,6 +575,19 @@ def floor_probes(hz, pb, steps, peak):
         out["stream_same_bytes_2_nodes_us"] = us
         out["stream_same_bytes_frac_of_peak"] = (pb.fwd_bytes + pb.bwd_bytes) / (us * 1e-6) / 1e9 / peak
 
+        # (4) the same bytes behind the two dependent round trips every fused kernel has (theta -> tap addresses -> bytes)
+        def chain_stream_step(i):
+            e = pb.sets[i % S]
+            xb = e["x"].numel() * 4
+            _lib.check(L.loans_stn_probe(3, ptr(e["x"]), ptr(e["gx"]), min(fr, xb) // 16 * 16, fw // 16 * 16, ctas, st()), "probe")
+            _lib.check(L.loans_stn_probe(3, ptr(e["x"]), ptr(e["gx"]), min(br, xb) // 16 * 16, bw // 16 * 16, ctas, st()), "probe")
+        g = graph_of(chain_stream_step, S)
+        for _ in range(3):
+            g.replay()
+        us = pb.per_launch(g, steps) * 1e3
+        out["chain_then_stream_2_nodes_us"] = us
+        out["chain_then_stream_frac_of_peak"] = (pb.fwd_bytes + pb.bwd_bytes) / (us * 1e-6) / 1e9 / peak
+
         def stream_one(i, rd, wr):
             e = pb.sets[i % S]
             _lib.check(L.loans_stn_probe(2, ptr(e["x"]), ptr(e["gx"]), min(rd, e["x"].numel() * 4) // 16 * 16, wr // 16 * 16, ctas, st()), "probe")
@@ -585,7 +598,8 @@ def floor_probes(hz, pb, steps, peak):
             out["stream_%s_bytes_1_node_us" % key] = pb.per_launch(g, steps) * 1e3
     out["note"] = ("per step of two graph nodes with the fused kernels' launch attributes (%d CTAs x 256 threads): empty kernels; two "
                    "dependent DRAM loads + a store per thread; the step's algorithmic bytes read / written as plain coalesced "
-                   "16-byte accesses.  The last one is what the roofline's denominator costs on this GPU at THIS size" % ctas)
+                   "16-byte accesses (what the roofline's denominator costs on this GPU at THIS size); the same bytes behind the two "
+                   "dependent round trips (chain_then_stream: an ideal fused step -- no arithmetic, no gather, no scatter)" % ctas)
     return out
 
 

@@ -37,7 +37,8 @@
 
 /* measurement aid of bench.py's "floor" block (stn_probe.cu): what a kernel of our launch shape costs before any STN
  * arithmetic -- mode 0 an empty kernel with our launch attributes, mode 1 two dependent DRAM round trips and a store,
- * mode 2 in_bytes read + out_bytes written as plain coalesced 16-byte accesses.  ctas x 256 threads on `stream`. */
+ * mode 2 in_bytes read + out_bytes written as plain coalesced 16-byte accesses, mode 3 the chain of mode 1 and then the bytes of
+ * mode 2 (an ideal fused kernel: same bytes, same two dependent round trips, no arithmetic).  ctas x 256 threads on `stream`. */
 #ifdef __cplusplus
 extern "C"
 #endif

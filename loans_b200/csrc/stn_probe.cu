@@ -5,7 +5,10 @@
 //   mode 1  chain:   per CTA one 4-byte load (as theta), then per thread one load whose address depends on it (as the
 //                    taps), then one store (as the crop): the two dependent DRAM round trips every fused kernel has;
 //   mode 2  stream:  in_bytes read and out_bytes written as plain coalesced 16-byte accesses, nothing else: the same
-//                    algorithmic bytes as a fused launch, moved by the simplest possible kernel of the same grid.
+//                    algorithmic bytes as a fused launch, moved by the simplest possible kernel of the same grid;
+//   mode 3  both:    the chain of mode 1 FIRST (a CTA cannot know which bytes to move before it has read theta and derived the
+//                    tap addresses), then mode 2's bytes, the reads offset by the chain's result: what an ideal fused kernel
+//                    of this grid costs -- same bytes, same two dependent round trips, no arithmetic.
 #include "../../include/loans_stn_devel.h"
 #include "stn_common.cuh"
 
@@ -45,6 +48,28 @@ __global__ void __launch_bounds__(kThreads) probe_stream_kernel(const float4 *in
     for (long long i = t0; i < n_out; i += stride) out[i] = z;
 }
 
+__global__ void __launch_bounds__(kThreads) probe_chain_stream_kernel(const float4 *in, float4 *out, long long n_in, long long n_out)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int *in1 = reinterpret_cast<const int *>(in);
+    const long long in_elems = n_in * 4;
+    const long long slot = ((long long)blockIdx.x * 32) % in_elems;
+    const int off = __ldg(in1 + slot);                                                    // hop 1 (theta)
+    const long long at = (slot + 8LL * threadIdx.x + (long long)(off & 1023) * 4096 + 2048) % in_elems;
+    const int hop2 = __ldg(in1 + at);                                                     // hop 2 (first taps)
+    const long long stride = (long long)gridDim.x * kThreads, t0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long skew = (hop2 == 0x7fffffff) ? 1 : 0;                                  // the stream depends on the chain; never taken
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = t0 + skew; i < n_in; i += stride) {
+        const float4 v = __ldg(in + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x == 1.2345e38f) acc.y = 1.f;
+    const float4 z = make_float4(0.f, 0.f, acc.y * 0.f, 0.f);
+    for (long long i = t0; i < n_out; i += stride) out[i] = z;
+}
+
 }  // namespace stn
 
 using namespace stn;
@@ -69,6 +94,9 @@ extern "C" int loans_stn_probe(int mode, const void *in, void *out, long long in
     } else if (mode == 2) {
         if ((in_bytes && !in) || (out_bytes && !out)) return set_error("loans_stn_probe: NULL buffer");
         e = cudaLaunchKernelEx(&cfg, probe_stream_kernel, (const float4 *)in, (float4 *)out, in_bytes / 16, out_bytes / 16);
+    } else if (mode == 3) {
+        if (!in || !out || in_bytes < (1 << 20)) return set_error("loans_stn_probe: chain + stream mode needs >= 1 MiB of input");
+        e = cudaLaunchKernelEx(&cfg, probe_chain_stream_kernel, (const float4 *)in, (float4 *)out, in_bytes / 16, out_bytes / 16);
     } else {
         return set_error("loans_stn_probe: unknown mode %d", mode);
     }
