@@ -293,6 +293,7 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
     if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.gx) & 15) != 0) return -1;
     if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
     if ((long long)p.H * p.W * p.C > 0x7fffffffLL) return -1;
+    if ((long long)p.K * p.C * p.oH * p.oW > 0x7fffffffLL) return -1;    // gy of one frame's crops is indexed with 32-bit integers
     const int frames = p.N / p.K;
     // a frame with a crop this path declines runs the general gx role: same tile geometry as launch_crop_bwd, vector stores
     {
