@@ -715,3 +715,57 @@ def test_device_loader_reads_the_reference_formats(T, tmp_path):
     assert labels[1].tolist() == [[0, 0, 48, 56], [2, 2, 25, 26]] and labels[2].tolist() == [7]
     img, label, dummy = lab[0]
     assert np.array_equal(img.cpu().numpy(), reference("a.png", size)) and label.tolist() == labels[0].tolist() and dummy.shape == (1,)
+
+
+@pytest.mark.parametrize("variant", ["gray", "gray_bf16", "nhwc4", "bf16", "corners"])
+def test_epilogues_through_the_row_owner_kernel(T, variant):
+    """Several crops per frame with gx (stn_kframe.cu) behind every crop format of the `_ex` entry points: the grayscale epilogue
+    (float32 and bf16 gy), bf16 crops planar and channels-last, and corner points with their upstream gradient -- forced on a
+    small batch (the automatic rule takes the kernel from 16 frames), against the oracle."""
+    from tests import gpu_util as G
+    from loans_b200 import _lib
+    from loans_b200.functions import stn_crop
+    from oracle import stn_numpy as on
+    wl = W.WORKLOADS["cfg4"]._replace(height=96, width=128, out_h=21, out_w=27)
+    k = wl.crops_per_frame
+    d = W.make_inputs(wl, batch=5, rotate=False)
+    d["theta"][:, 0, 0] *= 1.3                                            # steps of >= 2 frame pixels: every frame is taken
+    d["theta"][:, 1, 1] *= 1.3
+    osz = (wl.out_h, wl.out_w)
+    n = d["theta"].shape[0]
+    rng = np.random.default_rng(3)
+    x, th = _t(T, d["x"], grad=True), _t(T, d["theta"], grad=True)
+    try:
+        _lib.band_backward(True)
+        if variant.startswith("gray"):
+            dt = T.bfloat16 if variant == "gray_bf16" else T.float32
+            gg = rng.standard_normal((n, 1) + osz).astype(np.float32)
+            if dt == T.bfloat16:
+                gg = G.bf16_round(gg)
+            rois, _ = stn_crop(x, th, osz, mask01=0.0, crops_per_frame=k, out_dtype=dt, grayscale=True)
+            rois.backward(_t(T, gg).to(dt))
+            gy_eff, up = on.grayscale_backward(gg), None
+        elif variant == "nhwc4":
+            gy_r = G.bf16_round(d["gy"])
+            gy_cl = np.concatenate([np.transpose(gy_r, (0, 2, 3, 1)), np.full((n,) + osz + (1,), -7.0, np.float32)], axis=3)
+            rois, _ = stn_crop(x, th, osz, mask01=0.0, crops_per_frame=k, out_dtype=T.bfloat16, layout="nhwc4")
+            rois.backward(_t(T, gy_cl).to(T.bfloat16))
+            gy_eff, up = gy_r, None
+        elif variant == "bf16":
+            gy_r = G.bf16_round(d["gy"])
+            rois, _ = stn_crop(x, th, osz, mask01=0.0, crops_per_frame=k, out_dtype=T.bfloat16)
+            rois.backward(_t(T, gy_r).to(T.bfloat16))
+            gy_eff, up = gy_r, None
+        else:
+            gc = rng.standard_normal((n, 2, 2, 2)).astype(np.float32)
+            rois, pts = stn_crop(x, th, osz, mask01=0.0, crops_per_frame=k, points="corners")
+            T.autograd.backward([rois, pts], [_t(T, d["gy"]), _t(T, gc)])
+            up = np.zeros((n, 2) + osz, np.float32)
+            up[:, :, 0, 0], up[:, :, 0, -1], up[:, :, -1, 0], up[:, :, -1, -1] = gc[:, :, 0, 0], gc[:, :, 0, 1], gc[:, :, 1, 0], gc[:, :, 1, 1]
+            gy_eff = d["gy"]
+        assert _lib.last_kernel() == "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel"
+    finally:
+        _lib.band_backward(None)
+    gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, gy_eff, up, 0.0, k)
+    assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
+    assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())
