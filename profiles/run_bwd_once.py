@@ -22,7 +22,7 @@ gy = torch.from_numpy(d["gy"]).to(dev).to(ydt)
 gt = torch.empty((N, 2, 3), dtype=torch.float32, device=dev)
 gx = torch.empty((B, C, H, Wd), dtype=torch.float32, device=dev)
 _lib.band_tuning(variant=a[0], cs=a[1], rows=a[2], tile_kb=a[3])
-_lib.band_backward(len(sys.argv) <= 6 or a[4] != 0)
+_lib.band_backward(None if len(sys.argv) <= 6 else a[4] != 0)          # automatic dispatch unless the fifth knob is given
 for _ in range(4):
     _lib.check(_lib.lib().loans_stn_crop_bwd(x.data_ptr(), th.data_ptr(), 0.0, gy.data_ptr(), None, gt.data_ptr(), gx.data_ptr(), None,
                                              N, K, C, H, Wd, oH, oW, _lib.BF16 if ydt == torch.bfloat16 else _lib.F32,
