@@ -516,3 +516,45 @@ def test_benched_dispatch_at_full_size_against_the_oracle(G, name, need_gx, kern
     if need_gx:
         per_frame = np.abs(gx - gx0).reshape(batch, -1).max(axis=1) / np.abs(gx0).reshape(batch, -1).max(axis=1)
         assert per_frame.max() <= 2e-6, per_frame.max()
+
+
+def test_kframe_backward_random_shapes_against_the_general_kernel(G):
+    """Random shapes (1 / 3 / 4 channels, odd crop sizes up to 128 columns, 1 ... 6 crops per frame, frames down to 8 x 8) and random
+    upright boxes -- up- and down-sampling, mirrored, far outside the frame -- through the row-owner gx path (forced) and through
+    the general kernel: gx within the summation-order bar, gtheta within the gradient bar, every element of gx written."""
+    from loans_b200 import _lib
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        c = int(rng.choice([1, 3, 4]))
+        h, w = int(rng.integers(2, 40)) * 4, int(rng.integers(2, 40)) * 4
+        oh, ow = int(rng.integers(1, 40)), int(rng.integers(1, 129))
+        k = int(rng.integers(1, 7))
+        frames = int(rng.integers(1, 5))
+        n = frames * k
+        theta = np.zeros((n, 2, 3), np.float32)
+        theta[:, 0, 0] = rng.uniform(0.05, 1.4, n) * rng.choice([1, 1, 1, -1], n)
+        theta[:, 1, 1] = rng.uniform(0.05, 1.4, n)
+        theta[:, :, 2] = rng.uniform(-1.2, 1.2, (n, 2))
+        if case % 3 == 0:                                  # frames whose crops all step by >= 2 pixels: the path's own kernel
+            theta[:, 0, 0] = rng.uniform(2.2, 4.0, n) * max(ow - 1, 1) / (w - 1)
+            theta[:, 1, 1] = rng.uniform(2.2, 4.0, n) * max(oh - 1, 1) / (h - 1)
+        x = rng.random((frames, c, h, w), dtype=np.float32)
+        gy = rng.standard_normal((n, c, oh, ow), dtype=np.float32)
+        gg = rng.standard_normal((n, 2, oh, ow), dtype=np.float32)
+        try:
+            _lib.force_general(True)
+            gt0, gx0, ggo0 = G.crop_bwd(x, theta, (oh, ow), gy, gg, 0.0, k)
+        finally:
+            _lib.force_general(False)
+        try:
+            _lib.band_backward(True)
+            _lib.lib().loans_stn_configure(14, 1)          # LOANS_STN_CFG_KFRAME_SINGLE: also with one crop per frame
+            gt1, gx1, ggo1 = G.crop_bwd(x, theta, (oh, ow), gy, gg, 0.0, k)
+            assert _lib.last_kernel() == "stn_bwd_theta_tab_kernel+stn_bwd_kframe_kernel", (case, _lib.last_kernel())
+        finally:
+            _lib.lib().loans_stn_configure(14, 0)
+            _lib.band_backward(None)
+        assert not np.isnan(gx1).any(), case
+        assert np.array_equal(ggo0, ggo1), case
+        assert np.abs(gx1 - gx0).max() <= 2e-6 * max(np.abs(gx0).max(), 1e-30), (case, c, h, w, oh, ow, k)
+        assert np.abs(gt1 - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max()), case
