@@ -194,6 +194,64 @@ def test_against_torch_affine_grid_and_grid_sample(smooth):
     assert rel(gtheta, tt.grad.numpy()) < (1e-5 if smooth else 1e-4)
 
 
+def _forward_f64(x, theta, oh, ow):
+    """The operator as the reference's call sites define it (sheep/sheep_localizer.py:62-63; SURVEY.md 8a: align-corners pixel
+    map, zero padding), written independently of the oracle's statement sequence and in float64: for finite differences."""
+    b, c, h, w = x.shape
+    xs, ys = np.linspace(-1, 1, ow), np.linspace(-1, 1, oh)
+    out = np.zeros((b, c, oh, ow))
+    xp = np.pad(x.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    for n in range(b):
+        t = theta[n].astype(np.float64)
+        gx_ = t[0, 0] * xs[None, :] + t[0, 1] * ys[:, None] + t[0, 2]
+        gy_ = t[1, 0] * xs[None, :] + t[1, 1] * ys[:, None] + t[1, 2]
+        u = np.clip((gx_ + 1) * (w - 1) / 2 + 1, 0, w + 1)
+        v = np.clip((gy_ + 1) * (h - 1) / 2 + 1, 0, h + 1)
+        u0 = np.clip(np.floor(u).astype(int), 0, w)
+        v0 = np.clip(np.floor(v).astype(int), 0, h)
+        fu, fv = u - u0, v - v0
+        out[n] = (xp[n][:, v0, u0] * (1 - fu) * (1 - fv) + xp[n][:, v0, u0 + 1] * fu * (1 - fv) +
+                  xp[n][:, v0 + 1, u0] * (1 - fu) * fv + xp[n][:, v0 + 1, u0 + 1] * fu * fv)
+    return out
+
+
+@pytest.mark.parametrize("impl", [on, oc])
+def test_backward_is_the_derivative_of_the_forward(impl):
+    """What chainer's own tests of these two functions check (gradient_check.check_backward): the analytic gradients against
+    central differences of the forward -- here of an independent float64 forward, on smooth frames with every sample strictly
+    inside the frame (the operator is piecewise smooth: kinks sit on pixel centres and on the border), for theta and, the
+    operator being linear in x, as the exact adjoint identity <J d, gy> = <d, gx>."""
+    rng = np.random.default_rng(77)
+    b, c, h, w, oh, ow = 3, 3, 36, 44, 9, 11
+    x = W.make_frames(rng, b, c, h, w, smooth=True)
+    theta = np.zeros((b, 2, 3), np.float32)
+    theta[:, 0, 0] = rng.uniform(0.4, 0.7, b)
+    theta[:, 1, 1] = rng.uniform(0.4, 0.7, b)
+    theta[:, 0, 1] = rng.uniform(-0.1, 0.1, b)
+    theta[:, 1, 0] = rng.uniform(-0.1, 0.1, b)
+    theta[:, :, 2] = rng.uniform(-0.15, 0.15, (b, 2))
+    gy = rng.standard_normal((b, c, oh, ow)).astype(np.float32)
+    gtheta, gx, _ = impl.crop_backward(x, theta, (oh, ow), gy)
+    # theta: central differences of sum(gy * forward), step small against the distance to the next pixel centre for most samples
+    eps = 1e-6
+    num = np.zeros((b, 2, 3))
+    for n in range(b):
+        for idx in np.ndindex(2, 3):
+            tp, tm = theta.astype(np.float64).copy(), theta.astype(np.float64).copy()
+            tp[(n,) + idx] += eps
+            tm[(n,) + idx] -= eps
+            num[(n,) + idx] = ((_forward_f64(x[n:n + 1], tp[n:n + 1], oh, ow) - _forward_f64(x[n:n + 1], tm[n:n + 1], oh, ow)) * gy[n]).sum() / (2 * eps)
+    assert np.abs(gtheta - num).max() <= 1e-4 * np.abs(num).max()
+    # x: the forward is linear in x
+    d = rng.standard_normal(x.shape)
+    lhs = (_forward_f64(d, theta, oh, ow) * gy).sum()
+    rhs = (d * gx).sum()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    # and the float64 forward itself agrees with the oracle's forward
+    y, _ = impl.crop_forward(x, theta, (oh, ow))
+    assert np.abs(y - _forward_f64(x, theta, oh, ow)).max() <= 1e-5
+
+
 @pytest.mark.parametrize("impl", [on, oc])
 def test_gradients_on_affine_ramp_are_analytic(impl):
     # x = a*col + b*row + c  =>  y = a*u + b*v + c  =>  dy/du = a, dy/dv = b wherever the box is inside
