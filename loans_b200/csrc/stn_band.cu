@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                     const GT *gp = gyb + row * oW + j;
 #pragma unroll
                     for (int ch = 0; ch < CG; ++ch) {
+#ifndef STN_BAND_GXONLY                                  // A/B build (profiles/overlap_probe.py): gx alone, no taps, no gtheta
                         if (own) load_taps(xb + ch * plane, ta, W, px.v[ch][0], px.v[ch][1], px.v[ch][2], px.v[ch][3]);
+#endif
                         px.g[ch] = load_gy<GT, GRAY>(gp, ch, npx);
                     }
                 };
@@ -293,7 +295,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
                     }
                     TRACE(5);
 #pragma unroll
+#ifndef STN_BAND_GXONLY
                     for (int u = 0; u < ILP; ++u) rreduce(px[u]);
+#endif
                     TRACE(6);
                     // crop pixels of one column phase never share a frame pixel (lanes of one chunk are 32 columns apart from the next)
 #pragma unroll
@@ -496,7 +500,9 @@ __global__ void __launch_bounds__(kThreads, MINB) stn_bwd_band_kernel(const __gr
         }
         bulk_commit();
     }
-#ifndef STN_BAND_PULL_REDUCE
+#if defined(STN_BAND_GXONLY)
+    (void)s;
+#elif !defined(STN_BAND_PULL_REDUCE)
     reduce_gtheta_push(p, s, sm, n, rank, cs);
 #else
     reduce_gtheta(p, s, sm, n, rank, cs);

@@ -1,4 +1,4 @@
-"""Can the theta kernel (read-bound) and a gx-only row-band kernel (write-bound) overlap?  Uses an A/B build with
+"""Can the theta kernel (read-bound) and a gx-only row-band kernel (write-bound) overlap?  Uses an A/B build (profiles/ab_local.sh gxonly "-DSTN_BAND_GXONLY") with
 -DSTN_BAND_GXONLY (ab_builds/gxonly.so): crop_bwd with gx runs the gx-only band kernel, crop_bwd without gx the table-driven theta
 kernel; timed back to back on one stream and forked onto two streams (CUDA-graph replay).  usage: overlap_probe.py [cfg5 ...]"""
 import ctypes
