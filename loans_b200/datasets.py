@@ -126,7 +126,12 @@ class ImageDataset(object):
     def get_batch(self, indices):
         """float32 (B, 3, oH, oW) CUDA tensor in [0, 1] (frames of one size after the resize; a list of (3,H,W) tensors when
         image_size is None and the files differ in size)."""
-        imgs = self._frames([self._decode(i) for i in indices])
+        indices = list(indices)
+        return self.assemble_batch(indices, [self._decode(i) for i in indices])
+
+    def assemble_batch(self, indices, decoded):
+        """The batch of ``indices`` from their already decoded uint8 frames (the loader threads of ``MultithreadIterator``)."""
+        imgs = self._frames(decoded)
         if len({tuple(t.shape) for t in imgs}) == 1:
             return torch.stack(imgs)
         return imgs
@@ -176,7 +181,10 @@ class LabeledImageDataset(ImageDataset):
 
     def get_batch(self, indices):
         """(frames (B,3,oH,oW) CUDA float32, list of label arrays[, zeros (B,1)])."""
-        decoded = [self._decode(i) for i in indices]
+        indices = list(indices)
+        return self.assemble_batch(indices, [self._decode(i) for i in indices])
+
+    def assemble_batch(self, indices, decoded):
         labels = [self._label(i, f.shape[:2]) for i, f in zip(indices, decoded)]
         imgs = self._frames(decoded)
         frames = torch.stack(imgs) if len({tuple(t.shape) for t in imgs}) == 1 else imgs
@@ -195,4 +203,92 @@ class LabeledImageDataset(ImageDataset):
     __getitem__ = get_example
 
 
-__all__ = ["ImageDataset", "LabeledImageDataset", "read_image_listing", "read_labeled_listing", "decode_frame", "resize_bbox"]
+class MultithreadIterator(object):
+    """``chainer.iterators.MultithreadIterator(dataset, batch_size, repeat=True, shuffle=True, n_threads=1)`` as the reference
+    drives its datasets (train_sheep_localizer.py:113-116), for the datasets above: the files of a batch are decoded by
+    ``n_threads`` loader threads (PIL releases the GIL while it inflates a PNG), the NEXT batch is being decoded while the
+    current one is consumed, and ``next()`` returns the batch already assembled on the device -- what
+    ``concat_examples(batch, device)`` would give the updater: ``dataset.get_batch``'s result.
+
+    Epoch bookkeeping as chainer's iterators: ``epoch``, ``is_new_epoch``, ``epoch_detail``, ``previous_epoch_detail``,
+    ``reset()``; the order is a fresh ``numpy.random.permutation`` per epoch when ``shuffle``; with ``repeat`` a batch that
+    reaches the end of an epoch is filled up from the next epoch's order, without it the last batch is short and the next
+    call raises ``StopIteration``."""
+
+    def __init__(self, dataset, batch_size, repeat=True, shuffle=True, n_threads=1):
+        from concurrent.futures import ThreadPoolExecutor
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self._repeat, self._shuffle = bool(repeat), bool(shuffle)
+        self._pool = ThreadPoolExecutor(max_workers=max(1, int(n_threads)))
+        self.reset()
+
+    def reset(self):
+        self.current_position = 0
+        self.epoch = 0
+        self.is_new_epoch = False
+        self._previous_epoch_detail = -1.0
+        n = len(self.dataset)
+        self._order = np.random.permutation(n) if self._shuffle else None
+        self._pending = None
+        self._prefetch()
+
+    @property
+    def epoch_detail(self):
+        return self.epoch + self.current_position / len(self.dataset)
+
+    @property
+    def previous_epoch_detail(self):
+        return None if self._previous_epoch_detail < 0 else self._previous_epoch_detail
+
+    def _next_indices(self):
+        """Indices of the next batch and the iterator state behind it (chainer's SerialIterator arithmetic)."""
+        n = len(self.dataset)
+        if not self._repeat and self.epoch > 0:
+            return None
+        i, i_end = self.current_position, self.current_position + self.batch_size
+        order = self._order
+        idx = list(range(i, min(i_end, n))) if order is None else [int(v) for v in order[i:i_end]]
+        state = {"epoch": self.epoch, "is_new_epoch": False, "order": order, "position": i_end}
+        if i_end >= n:
+            state["epoch"] += 1
+            state["is_new_epoch"] = True
+            state["position"] = 0
+            if self._repeat:
+                rest = i_end - n
+                if order is not None:
+                    state["order"] = np.random.permutation(n)
+                if rest > 0:
+                    idx += list(range(rest)) if order is None else [int(v) for v in state["order"][:rest]]
+                    state["position"] = rest
+        return idx, state
+
+    def _prefetch(self):
+        nxt = self._next_indices()
+        if nxt is None:
+            self._pending = None
+            return
+        idx, state = nxt
+        futures = [self._pool.submit(self.dataset._decode, i) for i in idx]
+        self._pending = (idx, state, futures)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._pending is None:
+            raise StopIteration
+        idx, state, futures = self._pending
+        decoded = [f.result() for f in futures]
+        self._previous_epoch_detail = self.epoch_detail
+        self.epoch, self.is_new_epoch, self._order, self.current_position = state["epoch"], state["is_new_epoch"], state["order"], state["position"]
+        self._prefetch()                                    # the loader threads start on the next batch now
+        return self.dataset.assemble_batch(idx, decoded)
+
+    next = __next__
+
+    def finalize(self):
+        self._pool.shutdown(wait=False)
+
+
+__all__ = ["ImageDataset", "LabeledImageDataset", "MultithreadIterator", "read_image_listing", "read_labeled_listing", "decode_frame", "resize_bbox"]

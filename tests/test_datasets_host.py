@@ -82,3 +82,43 @@ def test_no_cpu_fallback_and_unsupported_modes(tmp_path):
         ds.ImageDataset(["a.png"], image_size=(8, 8), transform_probability=0.5)
     with pytest.raises(NotImplementedError):
         ds.ImageDataset(["a.png"], image_size=(8, 8), image_mode='L')
+
+
+class _FakeDataset(object):
+    """Stands in for the device datasets: the iterator only needs __len__, _decode and assemble_batch."""
+
+    def __init__(self, n):
+        self.n = n
+        self.decoded = []
+
+    def __len__(self):
+        return self.n
+
+    def _decode(self, i):
+        self.decoded.append(i)
+        return -i
+
+    def assemble_batch(self, indices, decoded):
+        assert decoded == [-i for i in indices]
+        return list(indices)
+
+
+def test_multithread_iterator_epoch_semantics():
+    """chainer.iterators.MultithreadIterator as the reference uses it (train_sheep_localizer.py:113-116): order, epoch counters,
+    the wrap of a repeating iterator into the next epoch's order, the short last batch and StopIteration without repeat."""
+    it = ds.MultithreadIterator(_FakeDataset(7), 3, repeat=False, shuffle=False, n_threads=3)
+    seen = [(b, it.epoch, it.is_new_epoch, round(it.epoch_detail, 4)) for b in it]
+    assert seen == [([0, 1, 2], 0, False, 0.4286), ([3, 4, 5], 0, False, 0.8571), ([6], 1, True, 1.0)]
+    with pytest.raises(StopIteration):
+        next(it)
+    it.reset()
+    assert next(it) == [0, 1, 2] and it.previous_epoch_detail == 0.0
+    np.random.seed(4)
+    it = ds.MultithreadIterator(_FakeDataset(5), 2, repeat=True, shuffle=True, n_threads=2)
+    batches = [next(it) for _ in range(5)]                                  # two epochs of five
+    flat = [i for b in batches for i in b]
+    assert sorted(flat[:5]) == [0, 1, 2, 3, 4] and sorted(flat[5:]) == [0, 1, 2, 3, 4]
+    assert it.epoch == 2 and it.is_new_epoch and it.current_position == 0
+    it = ds.MultithreadIterator(_FakeDataset(4), 3, repeat=True, shuffle=False)
+    assert [next(it) for _ in range(3)] == [[0, 1, 2], [3, 0, 1], [2, 3, 0]]
+    assert it.epoch == 2 and it.current_position == 1

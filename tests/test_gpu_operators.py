@@ -715,6 +715,12 @@ def test_device_loader_reads_the_reference_formats(T, tmp_path):
     assert labels[1].tolist() == [[0, 0, 48, 56], [2, 2, 25, 26]] and labels[2].tolist() == [7]
     img, label, dummy = lab[0]
     assert np.array_equal(img.cpu().numpy(), reference("a.png", size)) and label.tolist() == labels[0].tolist() and dummy.shape == (1,)
+    # the reference's iterator (train_sheep_localizer.py:113-116): loader threads decode, batches arrive on the device
+    it = ds.MultithreadIterator(d, 2, repeat=False, shuffle=False, n_threads=3)
+    got = [b for b in it]
+    assert [tuple(b.shape) for b in got] == [(2, 3) + size, (2, 3) + size, (1, 3) + size] and it.epoch == 1
+    assert np.array_equal(T.cat(got).cpu().numpy(), batch.cpu().numpy())
+    it.finalize()
 
 
 @pytest.mark.parametrize("variant", ["gray", "gray_bf16", "nhwc4", "bf16", "corners"])
