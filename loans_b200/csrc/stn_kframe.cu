@@ -288,6 +288,9 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
     // measured against the general kernel at BASELINE config 4's shapes: 128 us vs 155 us with 32 frames, 311-349 vs 541 us with
     // 128; 50 vs 45 us with 8 frames and 32 vs 29 us with 2 (two launches, tables of every crop per CTA): taken from 16 frames
     if (by_measurement && p.N / p.K < 16) return -1;
+    // the gx kernel takes a frame only if every crop on it steps by >= ~2 frame pixels per crop pixel (other frames run the
+    // general role inside the launch, at the general kernel's speed): by default only where a box of half the frame still does
+    if (by_measurement && ((p.oW > 1 && (p.W - 1) < 4 * (p.oW - 1)) || (p.oH > 1 && (p.H - 1) < 4 * (p.oH - 1)))) return -1;
     if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
     if (p.oW > 128) return -1;                                            // a crop row is held in registers, 32 columns per lane slot
     if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.gx) & 15) != 0) return -1;
