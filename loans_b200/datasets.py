@@ -160,13 +160,13 @@ class LabeledImageDataset(ImageDataset):
 
     @staticmethod
     def check_for_bad_label(label, image_size):
-        error_text = ("Label can not be scaled correctly are you sure you created the dataset correctly, and provided the "
-                      "correct sizes? Image size: %s, label: %s" % (image_size, label))
-        extra = [size * 0.1 for size in image_size]
-        assert (label[:, 0] >= 0 - extra[0]).all(), error_text
-        assert (label[:, 1] >= 0 - extra[1]).all(), error_text
-        assert (label[:, 2] <= image_size[0] + extra[0]).all(), error_text
-        assert (label[:, 3] <= image_size[1] + extra[1]).all(), error_text
+        """Boxes must lie inside the frame they were annotated on, give or take a tenth of its size (reference :143-149: an
+        AssertionError with the sizes in its message, raised before the boxes are scaled)."""
+        h, w = image_size
+        low = np.array([-0.1 * h, -0.1 * w]), np.array([1.1 * h, 1.1 * w])
+        inside = (label[:, 0:2] >= low[0]).all() and (label[:, 2:4] <= low[1]).all()
+        assert inside, ("Label can not be scaled correctly are you sure you created the dataset correctly, and provided the "
+                        "correct sizes? Image size: %s, label: %s" % (image_size, label))
 
     def _label(self, i, frame_hw):
         label = np.array(self._pairs[i][1], dtype=self._label_dtype)
