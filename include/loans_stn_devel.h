@@ -6,7 +6,8 @@
  * pick at other sizes):
  *   LOANS_STN_CFG_BAND_CS / _ROWS / _TILE_KB / _VARIANT: CTAs per crop, crop rows per band, shared-memory tile budget in
  *   KiB, kernel variant (1: CTA bands, 3: row bands) of the band backward; 0 = automatic.
- *   LOANS_STN_CFG_KFRAME_ROWS: frame rows per CTA of the several-crops-per-frame gx kernel (stn_kframe.cu); 0 = automatic.
+ *   LOANS_STN_CFG_KFRAME_ROWS: frame rows per CTA of the several-crops-per-frame gx kernel (stn_kframe.cu); 0 = automatic
+ *     (bits 16 and up: KiB of shared-memory padding per CTA instead of the automatic residency rule).
  *   LOANS_STN_CFG_KFRAME_SINGLE != 0: that kernel (theta kernel + row-owner gx) also for ONE crop per frame, ahead of the band
  *     backward (A/B arm).
  *

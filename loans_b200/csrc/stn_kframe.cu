@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 3) stn_bwd_kframe_kernel(const __gri
     q += (sizeof(KfCrop) * K + 15) & ~(size_t)15;
     KfCol *coltab = reinterpret_cast<KfCol *>(q);
     KfCol *rowtab = coltab + (size_t)K * oW;
-    int *rowinv = reinterpret_cast<int *>(rowtab + (size_t)K * oH);
+    short *rowinv = reinterpret_cast<short *>(rowtab + (size_t)K * oH);          // 2 * crop row + tap row, 16 bits (oH < 16384: launcher)
     float *xs = reinterpret_cast<float *>(q);
     float *ys = xs + oW;
     ScatterGeom *geom = reinterpret_cast<ScatterGeom *>(q + sizeof(float) * ((oW + oH + 3) & ~3));
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(kThreads, 3) stn_bwd_kframe_kernel(const __gri
         kc.code = a.code;
         rowtab[e] = kc;
         const int t0 = (a.code & kAxIdxMask) - 1 - r0;                  // band row of tap row 0 (tap row 1: + 1)
-        if ((a.code & kAxTap0) && t0 >= 0 && t0 < nr) rowinv[kk * rows + t0] = 2 * i;
-        if ((a.code & kAxTap1) && t0 + 1 >= 0 && t0 + 1 < nr) rowinv[kk * rows + t0 + 1] = 2 * i + 1;
+        if ((a.code & kAxTap0) && t0 >= 0 && t0 < nr) rowinv[kk * rows + t0] = (short)(2 * i);
+        if ((a.code & kAxTap1) && t0 + 1 >= 0 && t0 + 1 < nr) rowinv[kk * rows + t0 + 1] = (short)(2 * i + 1);
     }
     __syncthreads();
 
@@ -277,8 +277,9 @@ static cudaError_t launch_kframe_tt(const CropParams &p, unsigned ctas, size_t s
     }
 }
 
-static int g_kf_rows = 0;                                                // tuning knob (loans_stn_configure): 0 = automatic
-void kframe_tuning(int rows) { g_kf_rows = rows; }
+static int g_kf_rows = 0, g_kf_pad_kb = 0;                              // tuning knobs (loans_stn_configure): 0 = automatic
+// bits 0-15: frame rows per CTA; bits 16...: KiB of shared-memory padding instead of the automatic rule (A/B of the CTAs per SM)
+void kframe_tuning(int rows) { g_kf_rows = rows & 0xffff; g_kf_pad_kb = rows >> 16; }
 
 // Returns -1 when the call is not one this path takes (one crop per frame, frames without grad, channel count not 1 / 3 / 4,
 // unaligned rows): the caller then launches the general kernel.  Two launches: gtheta (table-driven theta kernel), then gx.
@@ -292,7 +293,7 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
     // general role inside the launch, at the general kernel's speed): by default only where a box of half the frame still does
     if (by_measurement && ((p.oW > 1 && (p.W - 1) < 4 * (p.oW - 1)) || (p.oH > 1 && (p.H - 1) < 4 * (p.oH - 1)))) return -1;
     if (p.C != 1 && p.C != 3 && p.C != 4) return -1;
-    if (p.oW > 128) return -1;                                            // a crop row is held in registers, 32 columns per lane slot
+    if (p.oW > 128 || p.oH > 16383) return -1;                                            // a crop row is held in registers, 32 columns per lane slot
     if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.gx) & 15) != 0) return -1;
     if (p.H > kAxIdxMask - 2 || p.W > kAxIdxMask - 2) return -1;
     if ((long long)p.H * p.W * p.C > 0x7fffffffLL) return -1;
@@ -328,12 +329,16 @@ int launch_crop_bwd_kframe(CropParams p, int gy_dtype, cudaStream_t stream, bool
     p.kf_rows_cta = rows;
     p.kf_ctas_per_frame = (p.H + rows - 1) / rows;
     p.band_fb_tiles_per_warp = (p.gx_tiles_per_frame + kWarps * p.kf_ctas_per_frame - 1) / (kWarps * p.kf_ctas_per_frame);
-    const size_t tables = sizeof(KfCol) * (size_t)p.K * (p.oW + p.oH) + sizeof(int) * (size_t)p.K * rows;
+    const size_t tables = sizeof(KfCol) * (size_t)p.K * (p.oW + p.oH) + ((sizeof(short) * (size_t)p.K * rows + 15) & ~(size_t)15);
     const size_t general = sizeof(float) * (size_t)((p.oW + p.oH + 3) & ~3) + sizeof(ScatterGeom) * (size_t)p.K;   // aliases the tables
     const size_t fixed = ((sizeof(KfCrop) * (size_t)p.K + 15) & ~(size_t)15) + (tables > general ? tables : general) + 16;
     const size_t region = sizeof(float) * (size_t)p.C * p.W * kWarps;
     p.kf_region_bytes = (int)(((region > (size_t)p.gx_tile_bytes ? region : (size_t)p.gx_tile_bytes) + 127) & ~(size_t)127);
-    const size_t smem = (size_t)p.kf_region_bytes + fixed;
+    size_t smem = (size_t)p.kf_region_bytes + fixed + (size_t)g_kf_pad_kb * 1024;
+    // several crops per frame: TWO CTAs per SM, not three.  Every gy row is read twice, by the warps that own the two frame rows
+    // it lands on; with two CTAs the SM keeps ~90 KB of L1 and the second read hits it, with three (216 KB of shared memory) 28 KB
+    // are left and it does not: 310-313 vs 367-370 us at BASELINE config 4 (no difference with one crop per frame: 172-177 us)
+    if (p.K > 1 && g_kf_pad_kb == 0 && smem < 77 * 1024) smem = 77 * 1024;
     if (smem > 200 * 1024) return -1;                                    // frame rows too wide or too many crops per frame
     const long long ctas = (long long)frames * p.kf_ctas_per_frame;
     if (ctas > 0x7fffffffLL) return -1;
