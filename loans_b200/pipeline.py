@@ -45,22 +45,65 @@ class HostCropPipeline(object):
             if self.uint8_frames:
                 from loans_b200.functions.ingest import FrameIngest
                 self.ingest = FrameIngest(b, (h, w), None, device=self.dev)
+            ydt = out_dtype
+            self._in_fields = [("xu8", (b, h, w, 3), torch.uint8) if self.uint8_frames else ("x", (b, c, h, w), torch.float32),
+                               ("theta", (n, 2, 3), torch.float32), ("gy", (n, c, oh, ow), ydt)]
+            self._out_fields = [("y", (n, c, oh, ow), ydt), ("grid", (n, 2, oh, ow), torch.float32), ("gtheta", (n, 2, 3), torch.float32)]
+            if need_gx:
+                self._out_fields.append(("gx", (b, c, h, w), torch.float32))
             for _ in range(self.depth):
-                self.slots.append({
-                    "xu8": torch.empty((b, h, w, 3), dtype=torch.uint8, device=self.dev) if self.uint8_frames else None,
-                    "x": torch.empty((b, c, h, w), device=self.dev), "theta": torch.empty((n, 2, 3), device=self.dev),
-                    "gy": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
-                    "y": torch.empty((n, c, oh, ow), dtype=out_dtype, device=self.dev),
-                    "grid": torch.empty((n, 2, oh, ow), device=self.dev), "gtheta": torch.empty((n, 2, 3), device=self.dev),
-                    "gx": torch.empty((b, c, h, w), device=self.dev) if need_gx else None,
-                    "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_out": torch.cuda.Event(), "used": False})
+                # inputs and outputs of a slot live in ONE device allocation each, so that a step whose host tensors are packed the
+                # same way (new_host_inputs / new_host_outputs) moves as one copy per direction instead of three and four
+                s_in, in_views = self._packed(self._in_fields, self.dev, False)
+                s_out, out_views = self._packed(self._out_fields, self.dev, False)
+                slot = {"xu8": None, "x": None, "gx": None, "in_packed": s_in, "out_packed": s_out,
+                        "ev_in": torch.cuda.Event(), "ev_run": torch.cuda.Event(), "ev_out": torch.cuda.Event(), "used": False}
+                slot.update(in_views)
+                slot.update(out_views)
+                if self.uint8_frames:
+                    slot["x"] = torch.empty((b, c, h, w), device=self.dev)
+                self.slots.append(slot)
         self.step = 0
         self.h2d_bytes = (1 if self.uint8_frames else 4) * b * c * h * w + 4 * n * 6 + n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4)
         self.d2h_bytes = n * c * oh * ow * (2 if out_dtype == torch.bfloat16 else 4) + 4 * (n * 2 * oh * ow + n * 6) \
             + (4 * b * c * h * w if need_gx else 0)
 
-    def submit(self, x_host, theta_host, gy_host, outputs, mask01=0.0):
-        """Enqueue one fwd+bwd step.  ``outputs``: dict with pinned host tensors 'y', 'grid', 'gtheta' and, if need_gx, 'gx'."""
+    @staticmethod
+    def _packed(fields, device, pinned):
+        """One uint8 allocation holding the fields back to back (256-byte aligned), and a dict of typed views into it."""
+        offs, total = [], 0
+        for _, shape, dt in fields:
+            offs.append(total)
+            nbytes = int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size()
+            total += (nbytes + 255) // 256 * 256
+        buf = torch.empty(total, dtype=torch.uint8, device=device)
+        if pinned:
+            buf = buf.pin_memory()
+        views = {}
+        for (name, shape, dt), off in zip(fields, offs):
+            nbytes = int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size()
+            views[name] = buf[off:off + nbytes].view(dt).view(shape)
+        return buf, views
+
+    def new_host_inputs(self):
+        """Pinned host tensors for one step's inputs ('x', 'theta', 'gy'), views of ONE pinned buffer laid out like the device
+        side: handed to submit() they upload as a single copy."""
+        buf, views = self._packed(self._in_fields, "cpu", True)
+        if self.uint8_frames:
+            views["x"] = views.pop("xu8")
+        views["_packed"] = buf
+        return views
+
+    def new_host_outputs(self):
+        """Pinned host tensors for one step's results ('y', 'grid', 'gtheta'[, 'gx']), views of ONE pinned buffer: one download."""
+        buf, views = self._packed(self._out_fields, "cpu", True)
+        views["_packed"] = buf
+        return views
+
+    def submit(self, x_host, theta_host, gy_host, outputs, mask01=0.0, inputs=None):
+        """Enqueue one fwd+bwd step.  ``outputs``: dict with pinned host tensors 'y', 'grid', 'gtheta' and, if need_gx, 'gx'.
+        ``inputs`` / ``outputs`` made by new_host_inputs() / new_host_outputs() travel as ONE copy per direction (``inputs`` then
+        replaces x_host / theta_host / gy_host, which may be None)."""
         b, k, c, h, w, oh, ow = self.dims
         n = b * k
         s = self.slots[self.step % self.depth]
@@ -69,9 +112,12 @@ class HostCropPipeline(object):
             with torch.cuda.stream(self.s_in):
                 if s["used"]:
                     self.s_in.wait_event(s["ev_out"])            # the slot's previous results have left the device
-                (s["xu8"] if self.uint8_frames else s["x"]).copy_(x_host, non_blocking=True)
-                s["theta"].copy_(theta_host, non_blocking=True)
-                s["gy"].copy_(gy_host, non_blocking=True)
+                if inputs is not None and inputs.get("_packed") is not None and inputs["_packed"].numel() == s["in_packed"].numel():
+                    s["in_packed"].copy_(inputs["_packed"], non_blocking=True)        # x | theta | gy in one transfer
+                else:
+                    (s["xu8"] if self.uint8_frames else s["x"]).copy_(x_host, non_blocking=True)
+                    s["theta"].copy_(theta_host, non_blocking=True)
+                    s["gy"].copy_(gy_host, non_blocking=True)
                 s["ev_in"].record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(s["ev_in"])
@@ -87,11 +133,14 @@ class HostCropPipeline(object):
                 s["ev_run"].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(s["ev_run"])
-                outputs["y"].copy_(s["y"], non_blocking=True)
-                outputs["grid"].copy_(s["grid"], non_blocking=True)
-                outputs["gtheta"].copy_(s["gtheta"], non_blocking=True)
-                if self.need_gx:
-                    outputs["gx"].copy_(s["gx"], non_blocking=True)
+                if outputs.get("_packed") is not None and outputs["_packed"].numel() == s["out_packed"].numel():
+                    outputs["_packed"].copy_(s["out_packed"], non_blocking=True)     # y | grid | gtheta [| gx] in one transfer
+                else:
+                    outputs["y"].copy_(s["y"], non_blocking=True)
+                    outputs["grid"].copy_(s["grid"], non_blocking=True)
+                    outputs["gtheta"].copy_(s["gtheta"], non_blocking=True)
+                    if self.need_gx:
+                        outputs["gx"].copy_(s["gx"], non_blocking=True)
                 s["ev_out"].record(self.s_out)
             s["used"] = True
 

@@ -775,3 +775,41 @@ def test_epilogues_through_the_row_owner_kernel(T, variant):
     gt0, gx0, _ = oc.crop_backward(d["x"], d["theta"], osz, gy_eff, up, 0.0, k)
     assert np.abs(th.grad.cpu().numpy() - gt0).max() <= 1e-4 * max(1.0, np.abs(gt0).max())
     assert np.abs(x.grad.cpu().numpy() - gx0).max() <= 2e-6 * max(1.0, np.abs(gx0).max())
+
+
+@pytest.mark.parametrize("uint8,need_gx,bf16", [(False, True, False), (True, False, False), (False, True, True)])
+def test_host_buffer_pipeline_packed_transfers(T, uint8, need_gx, bf16):
+    """HostCropPipeline.new_host_inputs / new_host_outputs: a step's inputs and results as views of one pinned buffer each -- one
+    copy per direction -- give the bits of the per-tensor path (and of the oracle for crops and grid)."""
+    from loans_b200.pipeline import HostCropPipeline
+    wl = W.WORKLOADS["cfg1"]
+    osz = (wl.out_h, wl.out_w)
+    dt = T.bfloat16 if bf16 else T.float32
+    rng = np.random.default_rng(17)
+    res = {}
+    for packed in (True, False):
+        with HostCropPipeline(3, 3, wl.height, wl.width, osz, need_gx=need_gx, out_dtype=dt, depth=2, uint8_frames=uint8) as pipe:
+            steps = []
+            for i in range(3):
+                d = W.make_inputs(wl, seed=300 + i, batch=3)
+                xin = rng.integers(0, 256, (3, wl.height, wl.width, 3), dtype=np.uint8) if uint8 else d["x"]
+                gy = T.from_numpy(d["gy"]).to(dt)
+                if packed:
+                    hin, out = pipe.new_host_inputs(), pipe.new_host_outputs()
+                    hin["x"].copy_(T.from_numpy(xin)); hin["theta"].copy_(T.from_numpy(d["theta"])); hin["gy"].copy_(gy)
+                    pipe.submit(None, None, None, out, mask01=0.0, inputs=hin)
+                else:
+                    hin = {"x": T.from_numpy(xin).pin_memory(), "theta": T.from_numpy(d["theta"]).pin_memory(), "gy": gy.pin_memory()}
+                    out = {"y": T.empty((3, 3) + osz, dtype=dt).pin_memory(), "grid": T.empty((3, 2) + osz).pin_memory(),
+                           "gtheta": T.empty((3, 2, 3)).pin_memory(), "gx": T.empty((3, 3, wl.height, wl.width)).pin_memory() if need_gx else None}
+                    pipe.submit(hin["x"], hin["theta"], hin["gy"], out, mask01=0.0)
+                steps.append((xin, d, hin, out))
+            rng = np.random.default_rng(17) if packed else rng          # the same uint8 frames in both passes
+        res[packed] = steps
+    for (xin, d, _, a), (_, _, _, b) in zip(res[True], res[False]):
+        for k in ("y", "grid", "gtheta") + (("gx",) if need_gx else ()):
+            assert T.equal(a[k], b[k]), k
+        x = xin.transpose(0, 3, 1, 2).astype(np.float32) / np.float32(255) if uint8 else xin
+        y0, g0 = oc.crop_forward(x, d["theta"], osz, 0.0)
+        ref = T.from_numpy(y0).to(dt).float().numpy()
+        assert np.array_equal(a["y"].float().numpy(), ref) and np.array_equal(a["grid"].numpy(), g0)
