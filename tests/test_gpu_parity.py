@@ -558,3 +558,24 @@ def test_kframe_backward_random_shapes_against_the_general_kernel(G):
         assert np.array_equal(ggo0, ggo1), case
         assert np.abs(gx1 - gx0).max() <= 2e-6 * max(np.abs(gx0).max(), 1e-30), (case, c, h, w, oh, ow, k)
         assert np.abs(gt1 - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max()), case
+
+
+@pytest.mark.parametrize("shape", [(16, 3, 1080, 1920, 75, 75), (2, 3, 2304, 4096, 33, 128), (1, 1, 4, 32768, 3, 9)])
+def test_large_frames(G, shape):
+    """HD and larger frames (the reference extracts 1920x1080 video frames before the loader shrinks them): whatever kernels the
+    automatic dispatch picks at these row widths -- row buffers of 23 ... 48 KB per warp, or none that fit -- against the C oracle."""
+    from loans_b200 import _lib
+    b, c, h, w, oh, ow = shape
+    rng = np.random.default_rng(b + h)
+    x = rng.random((b, c, h, w), dtype=np.float32)
+    theta = W.make_theta(rng, b, rotate=False)
+    theta[:, 0, 1] = theta[:, 1, 0] = 0.0
+    gy = rng.standard_normal((b, c, oh, ow), dtype=np.float32)
+    y, grid = G.crop_fwd(x, theta, (oh, ow), 0.0, 1)
+    gt, gx, _ = G.crop_bwd(x, theta, (oh, ow), gy, None, 0.0, 1)
+    kern = _lib.last_kernel()
+    y0, grid0 = oc.crop_forward(x, theta, (oh, ow), 0.0)
+    gt0, gx0, _ = oc.crop_backward(x, theta, (oh, ow), gy, None, 0.0)
+    assert np.array_equal(y, y0) and np.array_equal(grid, grid0), kern
+    assert G.rel_max(gx, gx0) <= 2e-6, (kern, G.rel_max(gx, gx0))
+    assert np.abs(gt - gt0).max() <= GRAD_TOL * max(1.0, np.abs(gt0).max()), kern
